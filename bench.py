@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the bev_b200 hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A "step" is one pass of the batched warp over one synthetic batch.  The default workload is
+BASELINE.json configs[1]: 256 synthetic 1080p uint8 frames, one fixed homography (SURVEY.md 8d
+H_canon), bilinear image->BEV warp to 1024x1024.  N > 1 runs one process per GPU (torchrun), each
+with its own 256 frames (weak scaling, no data-path collective); rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "BEV warp Mpix/s"
+UNIT = "Mpix/s"
+
+# name -> (n_frames, src (w,h), dst (w,h), channels, dtype, flags, homography scale, inverse)
+WORKLOADS = {
+    "cfg2_1080p_to_bev1024_u8c3_bilinear_x256": (256, (1920, 1080), (1024, 1024), 3, "uint8", 1, 1, False),
+    "cfg2_nearest": (256, (1920, 1080), (1024, 1024), 3, "uint8", 0, 1, False),
+    "cfg1_single_frame": (1, (1920, 1080), (1024, 1024), 3, "uint8", 1, 1, False),
+    "cfg5_4k_to_bev2048_u8c3_x64": (64, (3840, 2160), (2048, 2048), 3, "uint8", 1, 2, False),
+    "cfg5_4k_to_bev2048_f16c3_x64": (64, (3840, 2160), (2048, 2048), 3, "float16", 1, 2, False),
+    "cfg5_inv_bev2048_to_4k_u8c3_x64": (64, (2048, 2048), (3840, 2160), 3, "uint8", 1, 2, True),
+    "cfg5_inv_bev2048_to_4k_f16c3_x64": (64, (2048, 2048), (3840, 2160), 3, "float16", 1, 2, True),
+}
+DEFAULT_WORKLOAD = "cfg2_1080p_to_bev1024_u8c3_bilinear_x256"
+
+
+def h_canon(scale):
+    """SURVEY.md 8d canonical homography (1080p -> 1024^2; x2 for 4K -> 2048^2)."""
+    from bev_b200 import homo
+    src = np.array([[700, 420], [1220, 420], [1900, 1060], [20, 1060]], np.float64) * scale
+    dst = np.array([[200, 0], [824, 0], [824, 1024], [200, 1024]], np.float64) * scale
+    return homo.homo_from_pts(src, dst)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples taken while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "20"], stdout=f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.05)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 7:
+                    continue
+                try:
+                    sm.append(float(parts[0]))
+                    mx.append(float(parts[1]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, parts[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def reference_arm(args, wl):
+    """--impl reference: the reference's CPU implementation (cv2 loop, all host threads) on a
+    bounded sample of the same workload.  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import ref_cpu
+    from oracle.synth import seeded_frame
+    n_frames, ssize, dsize, ch, dtype, flags, hscale, inverse = WORKLOADS[wl]
+    H = h_canon(hscale)
+    if inverse:
+        H = np.linalg.inv(H)
+    sample = min(n_frames, 32)
+    np_dtype = "float32" if dtype == "float16" else dtype  # cv2 has no fp16 warp
+    frames = [seeded_frame(1234 + i, ssize[1], ssize[0], ch, np_dtype) for i in range(sample)]
+    run, kind, cores = ref_cpu.make_warp_runner()
+    for _ in range(max(args.warmup, 1)):
+        run(frames[:4], H, dsize, flags)
+    times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        run(frames, H, dsize, flags)
+        times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    value = sample * dsize[0] * dsize[1] / (ms * 1e-3) / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8" if dtype == "uint8" else dtype,
+        "data": "synthetic",
+        "config": {"workload": wl, "frames_per_step": sample, "src": list(ssize), "dst": list(dsize),
+                   "note": "each step = the reference loop (cv2.warpPerspective per frame, "
+                           "vis_homo.py:85-89) over a %d-frame sample of the workload" % sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": "%d steps x %d frames" % (args.steps, sample),
+                         "cpu": ref_cpu.cpu_model()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    from bev_b200 import _native, homo, sharding
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n_frames, ssize, dsize, ch, dtype, flags, hscale, inverse = WORKLOADS[wl]
+    H = h_canon(hscale)
+    if inverse:
+        H = np.linalg.inv(H)
+    if args.path:
+        _native.set_warp_path(args.path)
+    tdtype = {"uint8": torch.uint8, "float16": torch.float16, "float32": torch.float32}[dtype]
+    es = {"uint8": 1, "float16": 2, "float32": 4}[dtype]
+
+    # synthetic frames: i.i.d. uniform noise, generated on the device, per-rank seed
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    frames = torch.randint(0, 256, (n_frames, ssize[1], ssize[0], ch), dtype=torch.uint8, device=dev,
+                           generator=g)
+    if tdtype != torch.uint8:
+        frames = (frames.to(torch.float32) / 255.0).to(tdtype)
+    out = torch.empty((n_frames, dsize[1], dsize[0], ch), dtype=tdtype, device=dev)
+
+    T, r0, r1 = _native.warp_touched_pixels(ssize, dsize, H, flags)
+    algo_bytes_frame = (T + dsize[0] * dsize[1]) * ch * es
+    algo_bytes_step = algo_bytes_frame * n_frames
+
+    def step():
+        homo.warp_perspective(frames, H, dsize, dst=out, flags=flags)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.05)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    ms_per_step = total_ms_max / args.steps
+    px_step = n_frames * dsize[0] * dsize[1]
+    value = world * px_step / (ms_per_step * 1e-3) / 1e6
+
+    # ---- e2e: same metric through the host-buffer C-ABI call, pinned host memory, H2D + D2H timed
+    e2e_steps = max(1, min(args.e2e_steps, args.steps))
+    h_src = torch.empty(frames.shape, dtype=tdtype).pin_memory()
+    h_src.copy_(frames)
+    h_dst = torch.empty(out.shape, dtype=tdtype).pin_memory()
+    _native.warp_perspective_host(h_src, H, dsize, dst=h_dst, flags=flags)  # warm-up (allocs)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        _native.warp_perspective_host(h_src, H, dsize, dst=h_dst, flags=flags)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * px_step / float(te.item()) / 1e6
+    row_bytes = ssize[0] * ch * es
+    up0, up1 = _native.warp_host_rows(ssize, dsize, H, flags)  # only referenced rows are uploaded
+    h2d = n_frames * (up1 - up0 + 1) * row_bytes
+    d2h = out.numel() * es
+
+    # ---- gather of BEV outputs to rank 0 (reported separately from the warp scaling)
+    gather = None
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        gathered = sharding.gather_to_rank0(out)
+        g1.record()
+        torch.cuda.synchronize()
+        tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        gms = float(tg.item())
+        gather = {"ms": gms, "bytes_into_rank0": (world - 1) * out.numel() * es,
+                  "GBps_into_rank0": (world - 1) * out.numel() * es / (gms * 1e-3) / 1e9}
+        del gathered
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        launch_ms = statistics.mean(per_launch_ms)
+        achieved = algo_bytes_step / (launch_ms * 1e-3) / 1e9
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(prof):
+            try:
+                traffic = json.load(open(prof)).get(wl)
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8" if dtype == "uint8" else dtype,
+            "data": "synthetic",
+            "config": {"workload": wl, "frames_per_gpu": n_frames, "src": list(ssize),
+                       "dst": list(dsize), "channels": ch,
+                       "interp": "bilinear" if flags & 1 else "nearest",
+                       "homography": "H_canon (SURVEY 8d)", "parallelism": "frames sharded, %d per GPU" % n_frames,
+                       "l2": "inputs %.0f MB per step >> 126 MB L2, no flush needed"
+                             % (frames.numel() * es / 1e6),
+                       "kernel_path": args.path or "auto"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "api": "bevk_warp_perspective_host (pinned host src/dst)"},
+            "gpu_launches": args.steps * 1,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algo_bytes_per_launch": algo_bytes_step,
+                         "algo_bytes_per_frame": algo_bytes_frame,
+                         "launch_ms": launch_ms, "kernel": "bevk warp kernel (1 launch per step)"},
+        }
+        if gather:
+            line["gather"] = gather
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import ref_cpu
+            sample = min(n_frames, 32)
+            host = frames[:sample].cpu()
+            if tdtype == torch.float16:
+                host = host.to(torch.float32)
+            cb = ref_cpu.time_warp(list(host.numpy()), H, tuple(dsize), flags,
+                                   min_seconds=args.cpu_seconds)
+            line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"],
+                                    "kind": cb["kind"], "sample": cb["sample"], "cpu": cb["cpu"],
+                                    "ms_per_frame": cb["ms_per_frame"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--path", default=None, choices=[None, "auto", "generic", "fast"])
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        reference_arm(args, args.workload)
+        return
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # convenience: relaunch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+               "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
+               "--master-port", str(29500 + os.getpid() % 500)] + sys.argv
+        sys.exit(subprocess.call(cmd))
+    ours(args, args.workload)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,297 @@
+"""ctypes binding of libbev_b200.so (the C ABI declared in include/bev_b200.h).
+
+PyTorch is only the plumbing here -- device memory, the current CUDA stream -- and every compute
+call goes through the C ABI with raw pointers.  There is no CPU fallback: a missing library, a CPU
+tensor or a non-sm_100 device raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbev_b200.so")
+
+U8, F16, F32, F64 = 0, 1, 2, 3
+MODE = {"bev": 0, "world": 1}
+
+_lib = None
+
+_c_int = ctypes.c_int
+_c_i64 = ctypes.c_int64
+_vp = ctypes.c_void_p
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int)
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_fp = ctypes.POINTER(ctypes.c_float)
+
+# name -> (restype, argtypes); kept in step with include/bev_b200.h (tests/test_capi_symbols.py)
+SIGNATURES = {
+    "bevk_version": (_c_int, []),
+    "bevk_last_error": (ctypes.c_char_p, []),
+    "bevk_device_info": (_c_int, [_ip, _ip, _ip]),
+    "bevk_invert3x3": (_c_int, [_dp, _dp]),
+    "bevk_warp_perspective": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                       _c_int, _dp, _c_int, _i32p, _c_int, _c_int, _dp, _vp]),
+    "bevk_warp_perspective_host": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                            _c_int, _c_int, _dp, _c_int, _i32p, _c_int, _c_int,
+                                            _dp]),
+    "bevk_warp_host_rows": (_c_int, [_c_int, _c_int, _c_int, _c_int, _dp, _c_int, _c_int, _ip]),
+    "bevk_warp_set_path": (_c_int, [_c_int]),
+    "bevk_warp_touched_pixels": (_c_i64, [_c_int, _c_int, _c_int, _c_int, _dp, _c_int, _ip]),
+    "bevk_pts_project": (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _dp, _vp]),
+    "bevk_xywhr2xyxy": (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _dp, _vp]),
+    "bevk_xy82xywhr": (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _dp, _vp]),
+    "bevk_rbox_world_bev": (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _dp, _vp]),
+    "bevk_xywhr2xyvec": (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _vp]),
+    "bevk_xy82xyvec": (_c_int, [_vp, _vp, _c_i64, _c_int, _vp]),
+    "bevk_v2yaw": (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _vp]),
+    "bevk_yaw2v": (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _vp]),
+    "bevk_yaw2mat": (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _vp]),
+    "bevk_xywhr2xyxy_host": (_c_int, [_fp, _fp, _c_i64, _c_int, _dp]),
+    "bevk_xy82xywhr_host": (_c_int, [_fp, _fp, _c_i64, _c_int, _dp]),
+}
+
+
+class NativeError(RuntimeError):
+    """An entry point of libbev_b200.so returned an error code."""
+
+
+def lib():
+    """Load libbev_b200.so (once).  Raises if it has not been built -- never falls back."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "bev_b200: native library %s is missing. Build it with "
+                "`python -c 'import __graft_entry__ as g; g.build()'` or `make -C bev_b200/csrc`. "
+                "There is no CPU fallback." % LIB_PATH)
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        msg = lib().bevk_last_error().decode("utf-8", "replace")
+        if rc == -4:
+            # the reference raises AssertionError here (rbox_torch.py:140,161)
+            raise AssertionError(msg)
+        raise NativeError("%s failed (code %d): %s" % (what, rc, msg))
+
+
+def _mat(H, what="H"):
+    a = np.ascontiguousarray(_to_numpy(H), dtype=np.float64)
+    if a.shape != (3, 3):
+        raise ValueError("%s must be 3x3, got %s" % (what, a.shape))
+    return a
+
+
+def _to_numpy(a):
+    if hasattr(a, "detach"):  # torch tensor: homographies live on the host
+        if a.is_cuda:
+            a = a.cpu()       # explicit sync, same as the reference's assert on a CUDA H
+        return a.detach().numpy()
+    return np.asarray(a)
+
+
+def _dptr(a):
+    return a.ctypes.data_as(_dp)
+
+
+def invert3x3(H):
+    H = _mat(H)
+    M = np.empty((3, 3), np.float64)
+    lib().bevk_invert3x3(_dptr(H), _dptr(M))
+    return M
+
+
+def device_info():
+    sm, mj, mn = _c_int(), _c_int(), _c_int()
+    _check(lib().bevk_device_info(ctypes.byref(sm), ctypes.byref(mj), ctypes.byref(mn)),
+           "bevk_device_info")
+    return sm.value, mj.value, mn.value
+
+
+def _stream_ptr(t):
+    import torch
+    return _vp(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _require_cuda(t, what):
+    import torch
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor, got %s" % (what, type(t).__name__))
+    if not t.is_cuda:
+        raise RuntimeError("%s is on %s: bev_b200 runs on CUDA (sm_100a) only, there is no CPU "
+                           "fallback" % (what, t.device))
+
+
+def _warp_dtype(t):
+    import torch
+    code = {torch.uint8: U8, torch.float16: F16, torch.float32: F32}.get(t.dtype)
+    if code is None:
+        raise TypeError("warp_perspective supports uint8 / float16 / float32, got %s" % t.dtype)
+    return code
+
+
+def _prep_mats(M, n_frames, mat_index):
+    Ms = np.ascontiguousarray(_to_numpy(M), dtype=np.float64)
+    if Ms.ndim == 2:
+        Ms = Ms[None]
+    if Ms.ndim != 3 or Ms.shape[1:] != (3, 3):
+        raise ValueError("M must be 3x3 or (K,3,3), got %s" % (Ms.shape,))
+    idx = None
+    if mat_index is not None:
+        idx = np.ascontiguousarray(_to_numpy(mat_index), dtype=np.int32).reshape(-1)
+        if idx.shape[0] != n_frames:
+            raise ValueError("mat_index has %d entries for %d frames" % (idx.shape[0], n_frames))
+    elif Ms.shape[0] not in (1, n_frames):
+        raise ValueError("%d matrices for %d frames needs mat_index" % (Ms.shape[0], n_frames))
+    return Ms, idx
+
+
+def _border(borderValue):
+    b = np.zeros(4, np.float64)
+    v = np.atleast_1d(np.asarray(borderValue, dtype=np.float64)).reshape(-1)[:4]
+    b[:len(v)] = v  # cv2.Scalar semantics: missing channels are 0
+    return b
+
+
+def _frames_view(src):
+    """(N, H, W, C) view of a (H,W) / (H,W,C) / (N,H,W,C) tensor + how to undo it."""
+    if src.dim() == 2:
+        return src[None, :, :, None], lambda o: o[0, :, :, 0]
+    if src.dim() == 3:
+        return src[None], lambda o: o[0]
+    if src.dim() == 4:
+        return src, lambda o: o
+    raise ValueError("src must be (H,W), (H,W,C) or (N,H,W,C); got shape %s" % (tuple(src.shape),))
+
+
+def warp_perspective(src, M, dsize, dst=None, flags=1, borderMode=0, borderValue=0,
+                     mat_index=None):
+    import torch
+    _require_cuda(src, "src")
+    code = _warp_dtype(src)
+    s4, undo = _frames_view(src)
+    s4 = s4.contiguous()
+    n, h, w, c = s4.shape
+    dw, dh = int(dsize[0]), int(dsize[1])
+    Ms, idx = _prep_mats(M, n, mat_index)
+    if dst is not None:
+        _require_cuda(dst, "dst")
+        d4, _ = _frames_view(dst)
+        if tuple(d4.shape) != (n, dh, dw, c) or dst.dtype != src.dtype or not dst.is_contiguous() \
+                or dst.device != src.device:
+            raise ValueError("dst must be a contiguous %s tensor of shape %s on %s"
+                             % (src.dtype, (n, dh, dw, c), src.device))
+        out4 = d4
+    else:
+        out4 = torch.empty((n, dh, dw, c), dtype=src.dtype, device=src.device)
+    b = _border(borderValue)
+    with torch.cuda.device(src.device):
+        rc = lib().bevk_warp_perspective(
+            _vp(s4.data_ptr()), _vp(out4.data_ptr()), n, h, w, dh, dw, c, code, _dptr(Ms),
+            Ms.shape[0], idx.ctypes.data_as(_i32p) if idx is not None else None, int(flags),
+            int(borderMode), _dptr(b), _stream_ptr(src))
+    _check(rc, "bevk_warp_perspective")
+    return dst if dst is not None else undo(out4)
+
+
+def warp_perspective_host(src, M, dsize, dst=None, flags=1, borderMode=0, borderValue=0,
+                          mat_index=None):
+    """Host-buffer form: src / dst are numpy arrays or CPU tensors (pinned for full PCIe speed)."""
+    s = _to_numpy(src) if not isinstance(src, np.ndarray) else src
+    code = {np.dtype("uint8"): U8, np.dtype("float16"): F16, np.dtype("float32"): F32}.get(s.dtype)
+    if code is None:
+        raise TypeError("warp_perspective_host supports uint8/float16/float32, got %s" % s.dtype)
+    if s.ndim == 2:
+        s4, undo = s[None, :, :, None], (lambda o: o[0, :, :, 0])
+    elif s.ndim == 3:
+        s4, undo = s[None], (lambda o: o[0])
+    elif s.ndim == 4:
+        s4, undo = s, (lambda o: o)
+    else:
+        raise ValueError("src must be (H,W), (H,W,C) or (N,H,W,C)")
+    s4 = np.ascontiguousarray(s4)
+    n, h, w, c = s4.shape
+    dw, dh = int(dsize[0]), int(dsize[1])
+    Ms, idx = _prep_mats(M, n, mat_index)
+    if dst is None:
+        out4 = np.empty((n, dh, dw, c), s4.dtype)
+    else:
+        out4 = _to_numpy(dst) if not isinstance(dst, np.ndarray) else dst
+        out4 = out4.reshape(n, dh, dw, c)
+        if out4.dtype != s4.dtype or not out4.flags["C_CONTIGUOUS"]:
+            raise ValueError("dst must be C-contiguous with src's dtype")
+    b = _border(borderValue)
+    rc = lib().bevk_warp_perspective_host(
+        _vp(s4.ctypes.data), _vp(out4.ctypes.data), n, h, w, dh, dw, c, code, _dptr(Ms),
+        Ms.shape[0], idx.ctypes.data_as(_i32p) if idx is not None else None, int(flags),
+        int(borderMode), _dptr(b))
+    _check(rc, "bevk_warp_perspective_host")
+    return dst if dst is not None else undo(out4)
+
+
+def warp_touched_pixels(ssize, dsize, M, flags=1):
+    """(T, row_min, row_max) of SURVEY.md 8d, computed on the device."""
+    Mm = _mat(M, "M")
+    rr = (_c_int * 2)()
+    t = lib().bevk_warp_touched_pixels(int(ssize[1]), int(ssize[0]), int(dsize[1]), int(dsize[0]),
+                                       _dptr(Mm), int(flags), rr)
+    if t < 0:
+        _check(int(t), "bevk_warp_touched_pixels")
+    return int(t), int(rr[0]), int(rr[1])
+
+
+def warp_host_rows(ssize, dsize, M, flags=1):
+    """[first, last] source row that warp_perspective_host uploads for these matrices."""
+    Ms = np.ascontiguousarray(_to_numpy(M), dtype=np.float64).reshape(-1, 3, 3)
+    rr = (_c_int * 2)()
+    _check(lib().bevk_warp_host_rows(int(ssize[1]), int(ssize[0]), int(dsize[1]), int(dsize[0]),
+                                     _dptr(Ms), Ms.shape[0], int(flags), rr), "bevk_warp_host_rows")
+    return int(rr[0]), int(rr[1])
+
+
+def set_warp_path(path):
+    _check(lib().bevk_warp_set_path({"auto": 0, "generic": 1, "fast": 2}.get(path, path)),
+           "bevk_warp_set_path")
+
+
+# ----------------------------------------------------------------------------- projection plumbing
+
+def _proj_dtype(t):
+    import torch
+    code = {torch.float32: F32, torch.float64: F64}.get(t.dtype)
+    if code is None:
+        raise TypeError("projection kernels take float32 / float64 tensors, got %s" % t.dtype)
+    return code
+
+
+def rows_op(name, x, in_cols, out_shape_tail, *extra, H=None, has_H=False):
+    """Run a row-wise projection entry point: x (N, in_cols) -> (N, *out_shape_tail)."""
+    import torch
+    _require_cuda(x, "input")
+    code = _proj_dtype(x)
+    if in_cols == 1:
+        x2 = x.reshape(-1).contiguous()
+        n = x2.shape[0]
+    else:
+        if x.dim() != 2 or x.shape[1] != in_cols:
+            raise ValueError("%s expects shape (N, %d), got %s" % (name, in_cols, tuple(x.shape)))
+        x2 = x.contiguous()
+        n = x2.shape[0]
+    out = torch.empty((n,) + tuple(out_shape_tail), dtype=x.dtype, device=x.device)
+    args = [_vp(x2.data_ptr()), _vp(out.data_ptr()), n] + [int(e) for e in extra] + [code]
+    if has_H:
+        args.append(_dptr(_mat(H)) if H is not None else None)
+    with torch.cuda.device(x.device):
+        args.append(_stream_ptr(x))
+        rc = getattr(lib(), name)(*args)
+    _check(rc, name)
+    return out

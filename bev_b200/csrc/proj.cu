@@ -1,0 +1,453 @@
+// proj.cu -- batched 3x3 projection kernels for points and rotated boxes (sm_100a).
+//
+// Replaces the ~25 eager ATen launches per call of bev/rbox_torch.py (reference) and the numpy
+// passes of bev/rbox.py with ONE kernel per API function: every box / point is read once and
+// written once.  These kernels are HBM-bound (52 B per box); no tensor cores -- the work is a
+// per-element 2x2 rotate + 3x3 matvec + divide.
+//
+// Precision: tensors are float32 (or float64) in and out, but the geometry in between runs in
+// float64 registers (own range-reduced sincos, FMA matvec, one IEEE reciprocal per corner) and is
+// rounded once on output.  That is what keeps results within 1e-5 relative of the reference's
+// float64 numpy path near the horizon, where the reference's own float32 torch path is 2.3e-4 off
+// (SURVEY.md 0.5 / 8c).
+//
+// Layout: rows of 5 floats (20 B) are not 16 B aligned, so a block stages 256 rows through shared
+// memory with fully coalesced 4 B accesses on both sides; the row pitch in shared memory is odd
+// (W | 1 words) so the per-row reads are bank-conflict free.
+#include "bevk_common.cuh"
+
+namespace {
+
+constexpr int kRows = 256;  // rows per block iteration == threads per block
+
+struct Mat3 {
+    double h[9];
+};
+
+// ---- float64 helpers ----------------------------------------------------------------------------
+// sin/cos with |abs err| < 2e-11 for |x| < ~1e5: Cody-Waite reduction by pi/2 + Taylor kernels on
+// [-pi/4, pi/4].  ~22 DP ops instead of the ~120 of the fully accurate library sincos, which
+// would make the kernels FP64-bound.
+__device__ __forceinline__ void sincos_fast64(double x, double &s, double &c)
+{
+    const double k = rint(x * 0.63661977236758134308);  // 2/pi
+    double t = fma(k, -1.57079632679489655800e+00, x);  // pi/2 hi
+    t = fma(k, -6.12323399573676603587e-17, t);         // pi/2 lo
+    const double t2 = t * t;
+    double ps = fma(t2, -2.50521083854417187751e-08, 2.75573192239858906526e-06);  // -1/11!, 1/9!
+    ps = fma(ps, t2, -1.98412698412698412698e-04);                                // -1/7!
+    ps = fma(ps, t2, 8.33333333333333333333e-03);                                 //  1/5!
+    ps = fma(ps, t2, -1.66666666666666666667e-01);                                // -1/3!
+    ps = fma(ps * t2, t, t);
+    double pc = fma(t2, 2.08767569878680989792e-09, -2.75573192239858906526e-07);  // 1/12!, -1/10!
+    pc = fma(pc, t2, 2.48015873015873015873e-05);                                 //  1/8!
+    pc = fma(pc, t2, -1.38888888888888888889e-03);                                // -1/6!
+    pc = fma(pc, t2, 4.16666666666666666667e-02);                                 //  1/4!
+    pc = fma(pc, t2, -0.5);
+    pc = fma(pc, t2, 1.0);
+    const int q = (int)k & 3;
+    const double ss = (q & 1) ? pc : ps;
+    const double cc = (q & 1) ? ps : pc;
+    s = (q & 2) ? -ss : ss;
+    c = ((q + 1) & 2) ? -cc : cc;
+}
+
+template <typename T> struct Tr;
+template <> struct Tr<float> {
+    static __device__ __forceinline__ void sincos(double r, double &s, double &c) { sincos_fast64(r, s, c); }
+    static __device__ __forceinline__ double atan2(double y, double x) { return (double)atan2f((float)y, (float)x); }
+    static __device__ __forceinline__ double sqrt(double v) { return (double)sqrtf((float)v); }
+};
+template <> struct Tr<double> {
+    static __device__ __forceinline__ void sincos(double r, double &s, double &c) { ::sincos(r, &s, &c); }
+    static __device__ __forceinline__ double atan2(double y, double x) { return ::atan2(y, x); }
+    static __device__ __forceinline__ double sqrt(double v) { return ::sqrt(v); }
+};
+
+// [x, y, 1] through H with divide: one reciprocal, two multiplies
+__device__ __forceinline__ void project(const Mat3 &H, double x, double y, double &u, double &v)
+{
+    const double X = fma(H.h[0], x, fma(H.h[1], y, H.h[2]));
+    const double Y = fma(H.h[3], x, fma(H.h[4], y, H.h[5]));
+    const double W = fma(H.h[6], x, fma(H.h[7], y, H.h[8]));
+    const double r = 1.0 / W;
+    u = X * r;
+    v = Y * r;
+}
+
+// ---- per-row functors: in[] / out[] are float64 registers ------------------------------------
+struct FnCorners {  // xywhr -> 4 corners (+ optional homography)        rbox_torch.py:52-99
+    static constexpr int IN = 5, OUT = 8;
+    Mat3 H;
+    int mode, use_h;
+    template <typename T> __device__ __forceinline__ void operator()(const double *in, double *out) const
+    {
+        double s, c;
+        Tr<T>::sincos(in[4], s, c);
+        const double hw = in[2] * 0.5, hh = in[3] * 0.5;
+        // template (tl, bl, br, tr) and rotation sign layout per mode (rbox_torch.py:45-48,65-82)
+        double tx[4], ty[4], r01, r10;
+        if (mode == BEVK_MODE_BEV) {
+            tx[0] = -hw; ty[0] = -hh; tx[1] = -hw; ty[1] = hh;
+            tx[2] = hw;  ty[2] = hh;  tx[3] = hw;  ty[3] = -hh;
+            r01 = s; r10 = -s;
+        } else {
+            tx[0] = -hh; ty[0] = -hw; tx[1] = hh;  ty[1] = -hw;
+            tx[2] = hh;  ty[2] = hw;  tx[3] = -hh; ty[3] = hw;
+            r01 = -s; r10 = s;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double px = fma(c, tx[i], fma(r01, ty[i], in[0]));
+            const double py = fma(r10, tx[i], fma(c, ty[i], in[1]));
+            if (use_h)
+                project(H, px, py, out[2 * i], out[2 * i + 1]);
+            else {
+                out[2 * i] = px;
+                out[2 * i + 1] = py;
+            }
+        }
+    }
+};
+
+struct FnFromCorners {  // 4 corners (+ optional homography first) -> xywhr     rbox.py:50-63
+    static constexpr int IN = 8, OUT = 5;
+    Mat3 H;
+    int mode, use_h;
+    template <typename T> __device__ __forceinline__ void operator()(const double *in, double *out) const
+    {
+        double tlx = in[0], tly = in[1], blx = in[2], bly = in[3], trx = in[6], try_ = in[7];
+        if (use_h) {  // bottom-right (in[4], in[5]) is not used by the reference formula
+            project(H, in[0], in[1], tlx, tly);
+            project(H, in[2], in[3], blx, bly);
+            project(H, in[6], in[7], trx, try_);
+        }
+        const double wx = trx - tlx, wy = try_ - tly, hx = blx - tlx, hy = bly - tly;
+        out[0] = 0.5 * (blx + trx);
+        out[1] = 0.5 * (bly + try_);
+        out[2] = Tr<T>::sqrt(fma(wx, wx, wy * wy));
+        out[3] = Tr<T>::sqrt(fma(hx, hx, hy * hy));
+        const double vx = tlx - blx, vy = tly - bly;  // heading = tl - bl
+        out[4] = (mode == BEVK_MODE_BEV) ? Tr<T>::atan2(vx, vy) : Tr<T>::atan2(vy, vx);
+    }
+};
+
+struct FnSimilarity {  // rbox_world_bev                                   rbox_torch.py:123-168
+    static constexpr int IN = 5, OUT = 5;
+    Mat3 H;        // already divided by H[8] on the host
+    double scale;  // sqrt(H00^2 + H01^2)
+    int src_mode;
+    template <typename T> __device__ __forceinline__ void operator()(const double *in, double *out) const
+    {
+        double s, c;
+        Tr<T>::sincos(in[4], s, c);
+        // yaw2v(src): bev -> (sin, cos), world -> (cos, sin)
+        const double vx = (src_mode == BEVK_MODE_BEV) ? s : c;
+        const double vy = (src_mode == BEVK_MODE_BEV) ? c : s;
+        const double tx = fma(H.h[0], vx, H.h[1] * vy), ty = fma(H.h[3], vx, H.h[4] * vy);
+        // v2yaw(target): target is the other system
+        out[4] = (src_mode == BEVK_MODE_BEV) ? Tr<T>::atan2(ty, tx) : Tr<T>::atan2(tx, ty);
+        out[0] = fma(H.h[0], in[0], fma(H.h[1], in[1], H.h[2]));  // affine: no divide (:155-156)
+        out[1] = fma(H.h[3], in[0], fma(H.h[4], in[1], H.h[5]));
+        out[2] = in[2] * scale;
+        out[3] = in[3] * scale;
+    }
+};
+
+struct FnPts2 {  // pts_world_bev, (N,2)                                           rbox.py:136-151
+    static constexpr int IN = 2, OUT = 2;
+    Mat3 H;
+    template <typename T> __device__ __forceinline__ void operator()(const double *in, double *out) const
+    {
+        project(H, in[0], in[1], out[0], out[1]);
+    }
+};
+struct FnPts3 {  // pts_world_bev, homogeneous (N,3): third column comes back as w/w
+    static constexpr int IN = 3, OUT = 3;
+    Mat3 H;
+    template <typename T> __device__ __forceinline__ void operator()(const double *in, double *out) const
+    {
+        const double X = fma(H.h[0], in[0], fma(H.h[1], in[1], H.h[2] * in[2]));
+        const double Y = fma(H.h[3], in[0], fma(H.h[4], in[1], H.h[5] * in[2]));
+        const double W = fma(H.h[6], in[0], fma(H.h[7], in[1], H.h[8] * in[2]));
+        out[0] = X / W;
+        out[1] = Y / W;
+        out[2] = W / W;
+    }
+};
+struct FnXyvec {  // xywhr2xyvec                                              rbox_torch.py:101-112
+    static constexpr int IN = 5, OUT = 4;
+    int mode;
+    template <typename T> __device__ __forceinline__ void operator()(const double *in, double *out) const
+    {
+        double s, c;
+        Tr<T>::sincos(in[4], s, c);
+        const double dx = (mode == BEVK_MODE_BEV) ? s : c, dy = (mode == BEVK_MODE_BEV) ? c : s;
+        out[0] = in[0];
+        out[1] = in[1];
+        out[2] = fma(dx, in[3], in[0]);
+        out[3] = fma(dy, in[3], in[1]);
+    }
+};
+struct FnXy8vec {  // xy82xyvec                                               rbox_torch.py:114-121
+    static constexpr int IN = 8, OUT = 4;
+    template <typename T> __device__ __forceinline__ void operator()(const double *in, double *out) const
+    {
+        const double cx = 0.5 * (in[0] + in[4]), cy = 0.5 * (in[1] + in[5]);
+        out[0] = cx;
+        out[1] = cy;
+        out[2] = cx + (in[2] - in[0]);
+        out[3] = cy + (in[3] - in[1]);
+    }
+};
+struct FnV2yaw {  // rbox_torch.py:24-31
+    static constexpr int IN = 2, OUT = 1;
+    int mode;
+    template <typename T> __device__ __forceinline__ void operator()(const double *in, double *out) const
+    {
+        out[0] = (mode == BEVK_MODE_BEV) ? Tr<T>::atan2(in[0], in[1]) : Tr<T>::atan2(in[1], in[0]);
+    }
+};
+struct FnYaw2v {  // rbox_torch.py:33-40
+    static constexpr int IN = 1, OUT = 2;
+    int mode;
+    template <typename T> __device__ __forceinline__ void operator()(const double *in, double *out) const
+    {
+        double s, c;
+        Tr<T>::sincos(in[0], s, c);
+        out[0] = (mode == BEVK_MODE_BEV) ? s : c;
+        out[1] = (mode == BEVK_MODE_BEV) ? c : s;
+    }
+};
+struct FnYaw2mat {  // rbox_torch.py:42-50
+    static constexpr int IN = 1, OUT = 4;
+    int mode;
+    template <typename T> __device__ __forceinline__ void operator()(const double *in, double *out) const
+    {
+        double s, c;
+        Tr<T>::sincos(in[0], s, c);
+        out[0] = c;
+        out[3] = c;
+        out[1] = (mode == BEVK_MODE_BEV) ? s : -s;
+        out[2] = (mode == BEVK_MODE_BEV) ? -s : s;
+    }
+};
+
+// ---- the row kernel -----------------------------------------------------------------------------
+template <typename T, typename F>
+__global__ void __launch_bounds__(kRows) rows_kernel(const T *__restrict__ in, T *__restrict__ out,
+                                                     long long n, const __grid_constant__ F f)
+{
+    constexpr int IN = F::IN, OUT = F::OUT;
+    constexpr int PI = IN | 1, PO = OUT | 1;  // odd pitch: conflict-free row access
+    __shared__ T s_in[kRows * PI];
+    __shared__ T s_out[kRows * PO];
+    const long long n_blocks = (n + kRows - 1) / kRows;
+    for (long long b = blockIdx.x; b < n_blocks; b += gridDim.x) {
+        const long long row0 = b * kRows;
+        const int rows = (int)min((long long)kRows, n - row0);
+        const T *gin = in + row0 * IN;
+#pragma unroll
+        for (int k = 0; k < IN; ++k) {
+            const int i = k * kRows + threadIdx.x;
+            if (i < rows * IN) s_in[(i / IN) * PI + (i % IN)] = __ldg(gin + i);
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < rows) {
+            double a[IN], r[OUT];
+#pragma unroll
+            for (int k = 0; k < IN; ++k) a[k] = (double)s_in[threadIdx.x * PI + k];
+            f.template operator()<T>(a, r);
+#pragma unroll
+            for (int k = 0; k < OUT; ++k) s_out[threadIdx.x * PO + k] = (T)r[k];
+        }
+        __syncthreads();
+        T *gout = out + row0 * OUT;
+#pragma unroll
+        for (int k = 0; k < OUT; ++k) {
+            const int i = k * kRows + threadIdx.x;
+            if (i < rows * OUT) gout[i] = s_out[(i / OUT) * PO + (i % OUT)];
+        }
+        // the next iteration's s_in writes are ordered after this iteration's reads by the
+        // barrier above; s_out reads are ordered before the next writes by the next first barrier
+    }
+}
+
+template <typename F>
+int launch_rows(const void *in, void *out, int64_t n, int dtype, const F &f, cudaStream_t stream,
+                const char *name)
+{
+    int rc = bevk_require_device();
+    if (rc) return rc;
+    if (n < 0) BEVK_FAIL(BEVK_E_ARG, "%s: n must be >= 0", name);
+    if (n == 0) return BEVK_OK;  // empty input: no launch
+    if (!in || !out) BEVK_FAIL(BEVK_E_ARG, "%s: null buffer", name);
+    const long long n_blocks = (n + kRows - 1) / kRows;
+    // 8 resident blocks of 256 threads per SM; a whole number of waves when the batch is large
+    const long long max_grid = (long long)bevk_sm_count() * 8;
+    const int grid = (int)(n_blocks < max_grid ? n_blocks : max_grid);
+    if (dtype == BEVK_F32)
+        rows_kernel<float, F><<<grid, kRows, 0, stream>>>((const float *)in, (float *)out, n, f);
+    else if (dtype == BEVK_F64)
+        rows_kernel<double, F><<<grid, kRows, 0, stream>>>((const double *)in, (double *)out, n, f);
+    else
+        BEVK_FAIL(BEVK_E_ARG, "%s: dtype must be BEVK_F32 or BEVK_F64, got %d", name, dtype);
+    BEVK_CUDA(cudaGetLastError());
+    return BEVK_OK;
+}
+
+int check_mode(int mode, const char *name)
+{
+    if (mode != BEVK_MODE_BEV && mode != BEVK_MODE_WORLD)
+        BEVK_FAIL(BEVK_E_ARG, "%s: mode must be BEVK_MODE_BEV or BEVK_MODE_WORLD, got %d", name, mode);
+    return BEVK_OK;
+}
+
+void set_h(Mat3 &m, const double *H)
+{
+    for (int i = 0; i < 9; ++i) m.h[i] = H ? H[i] : (i % 4 == 0 ? 1.0 : 0.0);
+}
+
+}  // namespace
+
+extern "C" {
+
+int bevk_pts_project(const void *pts, void *out, int64_t n, int dim, int dtype, const double H[9],
+                     void *stream)
+{
+    if (!H) BEVK_FAIL(BEVK_E_ARG, "bevk_pts_project: H is null");
+    if (dim == 2) {
+        FnPts2 f;
+        set_h(f.H, H);
+        return launch_rows(pts, out, n, dtype, f, (cudaStream_t)stream, "bevk_pts_project");
+    }
+    if (dim == 3) {
+        FnPts3 f;
+        set_h(f.H, H);
+        return launch_rows(pts, out, n, dtype, f, (cudaStream_t)stream, "bevk_pts_project");
+    }
+    BEVK_FAIL(BEVK_E_ARG, "bevk_pts_project: dim must be 2 or 3, got %d", dim);
+}
+
+int bevk_xywhr2xyxy(const void *xywhr, void *xy8, int64_t n, int mode, int dtype, const double *H,
+                    void *stream)
+{
+    if (int rc = check_mode(mode, "bevk_xywhr2xyxy")) return rc;
+    FnCorners f;
+    set_h(f.H, H);
+    f.mode = mode;
+    f.use_h = H != nullptr;
+    return launch_rows(xywhr, xy8, n, dtype, f, (cudaStream_t)stream, "bevk_xywhr2xyxy");
+}
+
+int bevk_xy82xywhr(const void *xy8, void *xywhr, int64_t n, int mode, int dtype, const double *H,
+                   void *stream)
+{
+    if (int rc = check_mode(mode, "bevk_xy82xywhr")) return rc;
+    FnFromCorners f;
+    set_h(f.H, H);
+    f.mode = mode;
+    f.use_h = H != nullptr;
+    return launch_rows(xy8, xywhr, n, dtype, f, (cudaStream_t)stream, "bevk_xy82xywhr");
+}
+
+int bevk_rbox_world_bev(const void *xywhr_in, void *xywhr_out, int64_t n, int src_mode, int dtype,
+                        const double H[9], void *stream)
+{
+    if (int rc = check_mode(src_mode, "bevk_rbox_world_bev")) return rc;
+    if (!H) BEVK_FAIL(BEVK_E_ARG, "bevk_rbox_world_bev: H is null");
+    FnSimilarity f;
+    for (int i = 0; i < 9; ++i) f.H.h[i] = H[i] / H[8];  // rbox_torch.py:139
+    // the reference's two asserts (rbox_torch.py:140,161), checked on the host before any launch
+    if (!(fabs(f.H.h[6]) + fabs(f.H.h[7]) < 1e-5))
+        BEVK_FAIL(BEVK_E_AFFINE, "bevk_rbox_world_bev: H is not affine (|H20|+|H21| = %g)",
+                  fabs(f.H.h[6]) + fabs(f.H.h[7]));
+    const double s0 = sqrt(f.H.h[0] * f.H.h[0] + f.H.h[1] * f.H.h[1]);
+    const double s1 = sqrt(f.H.h[3] * f.H.h[3] + f.H.h[4] * f.H.h[4]);
+    if (!(fabs(s0 - s1) < 1e-5))
+        BEVK_FAIL(BEVK_E_AFFINE, "bevk_rbox_world_bev: H is not a similarity (scales %g vs %g)", s0, s1);
+    f.scale = s0;
+    f.src_mode = src_mode;
+    return launch_rows(xywhr_in, xywhr_out, n, dtype, f, (cudaStream_t)stream, "bevk_rbox_world_bev");
+}
+
+int bevk_xywhr2xyvec(const void *xywhr, void *xyvec, int64_t n, int mode, int dtype, void *stream)
+{
+    if (int rc = check_mode(mode, "bevk_xywhr2xyvec")) return rc;
+    FnXyvec f;
+    f.mode = mode;
+    return launch_rows(xywhr, xyvec, n, dtype, f, (cudaStream_t)stream, "bevk_xywhr2xyvec");
+}
+
+int bevk_xy82xyvec(const void *xy8, void *xyvec, int64_t n, int dtype, void *stream)
+{
+    FnXy8vec f;
+    return launch_rows(xy8, xyvec, n, dtype, f, (cudaStream_t)stream, "bevk_xy82xyvec");
+}
+
+int bevk_v2yaw(const void *v, void *yaw, int64_t n, int mode, int dtype, void *stream)
+{
+    if (int rc = check_mode(mode, "bevk_v2yaw")) return rc;
+    FnV2yaw f;
+    f.mode = mode;
+    return launch_rows(v, yaw, n, dtype, f, (cudaStream_t)stream, "bevk_v2yaw");
+}
+
+int bevk_yaw2v(const void *yaw, void *v, int64_t n, int mode, int dtype, void *stream)
+{
+    if (int rc = check_mode(mode, "bevk_yaw2v")) return rc;
+    FnYaw2v f;
+    f.mode = mode;
+    return launch_rows(yaw, v, n, dtype, f, (cudaStream_t)stream, "bevk_yaw2v");
+}
+
+int bevk_yaw2mat(const void *yaw, void *mat, int64_t n, int mode, int dtype, void *stream)
+{
+    if (int rc = check_mode(mode, "bevk_yaw2mat")) return rc;
+    FnYaw2mat f;
+    f.mode = mode;
+    return launch_rows(yaw, mat, n, dtype, f, (cudaStream_t)stream, "bevk_yaw2mat");
+}
+
+static int host_roundtrip(const float *in, float *out, int64_t n, int in_w, int out_w, int which,
+                          int mode, const double *H)
+{
+    int rc = bevk_require_device();
+    if (rc) return rc;
+    if (n == 0) return BEVK_OK;
+    if (!in || !out) BEVK_FAIL(BEVK_E_ARG, "host projection: null buffer");
+    float *d_in = nullptr, *d_out = nullptr;
+    cudaStream_t st;
+    BEVK_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    BEVK_CUDA(cudaMallocAsync(&d_in, (size_t)n * in_w * sizeof(float), st));
+    BEVK_CUDA(cudaMallocAsync(&d_out, (size_t)n * out_w * sizeof(float), st));
+    BEVK_CUDA(cudaMemcpyAsync(d_in, in, (size_t)n * in_w * sizeof(float), cudaMemcpyHostToDevice, st));
+    rc = which == 0 ? bevk_xywhr2xyxy(d_in, d_out, n, mode, BEVK_F32, H, st)
+                    : bevk_xy82xywhr(d_in, d_out, n, mode, BEVK_F32, H, st);
+    if (rc == BEVK_OK) {
+        cudaError_t e = cudaMemcpyAsync(out, d_out, (size_t)n * out_w * sizeof(float),
+                                        cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            bevk_set_error("host projection copy-back failed: %s", cudaGetErrorString(e));
+            rc = BEVK_E_CUDA;
+        }
+    }
+    cudaFreeAsync(d_in, st);
+    cudaFreeAsync(d_out, st);
+    cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+    return rc;
+}
+
+int bevk_xywhr2xyxy_host(const float *xywhr, float *xy8, int64_t n, int mode, const double *H)
+{
+    return host_roundtrip(xywhr, xy8, n, 5, 8, 0, mode, H);
+}
+
+int bevk_xy82xywhr_host(const float *xy8, float *xywhr, int64_t n, int mode, const double *H)
+{
+    return host_roundtrip(xy8, xywhr, n, 8, 5, 1, mode, H);
+}
+
+}  // extern "C"

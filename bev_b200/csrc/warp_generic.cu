@@ -1,0 +1,279 @@
+// warp_generic.cu -- direct-gather perspective warp for every dtype / channel count / border
+// value.  It is the catch-all behind bevk_warp_perspective: shapes the staged fast path
+// (warp_fast.cu) does not take land here.  One thread owns one dst pixel position, computes its
+// quantised source coordinate ONCE (FP64, the expensive part) and then loops over the frames of
+// its chunk, so the coordinate cost is amortised over the batch.
+//
+// Semantics: cv2.warpPerspective 4.13 (reference call sites vis_homo.py:89,91,
+// bev/tool/compo.py:38,46,47), restated in SURVEY.md Appendix A.
+#include "bevk_common.cuh"
+
+namespace {
+
+template <typename T> struct Px;
+template <> struct Px<uint8_t> {
+    static __device__ __forceinline__ float ld(const uint8_t *p) { return (float)__ldg(p); }
+};
+template <> struct Px<__half> {
+    static __device__ __forceinline__ float ld(const __half *p) { return __half2float(__ldg(p)); }
+};
+template <> struct Px<float> {
+    static __device__ __forceinline__ float ld(const float *p) { return __ldg(p); }
+};
+
+__device__ __forceinline__ const BevkWarpGroup &find_group(const BevkWarpParams &p, int z, int &gi)
+{
+    gi = 0;
+#pragma unroll 1
+    for (int i = 1; i < p.n_groups; ++i)
+        if (z >= p.g[i].chunk0) gi = i;
+    return p.g[gi];
+}
+
+__device__ __forceinline__ uint8_t border_u8(float b)
+{
+    // cv2: saturate_cast<uchar>(borderValue[c])
+    int v = __float2int_rn(b);
+    return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+// ---- bilinear ---------------------------------------------------------------------------------
+template <typename T, int C>
+__global__ void __launch_bounds__(256) warp_linear_kernel(const __grid_constant__ BevkWarpParams p)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= p.dst_w || y >= p.dst_h) return;
+    int gi;
+    const BevkWarpGroup &g = find_group(p, blockIdx.z, gi);
+    const int c_local = blockIdx.z - g.chunk0;
+    const int f0 = c_local * p.frames_per_chunk;
+    const int f1 = min(f0 + p.frames_per_chunk, g.count);
+
+    int X, Y;
+    bevk_map_pixel(g.M, x, y, p.bw0, 32.0, X, Y);
+    const int sx = bevk_sat16(X >> 5), sy = bevk_sat16(Y >> 5);
+    const int ax = X & 31, ay = Y & 31;
+    const bool cx0 = (sx >= 0 && sx < p.src_w), cx1 = (sx + 1 >= 0 && sx + 1 < p.src_w);
+    const bool cy0 = (sy >= 0 && sy < p.src_h), cy1 = (sy + 1 >= 0 && sy + 1 < p.src_h);
+    const bool in00 = cx0 && cy0, in01 = cx1 && cy0, in10 = cx0 && cy1, in11 = cx1 && cy1;
+    // element offsets inside a frame (only dereferenced when the tap is in range)
+    const long long o00 = ((long long)sy * p.src_w + sx) * C;
+    const long long o01 = o00 + C, o10 = o00 + (long long)p.src_w * C, o11 = o10 + C;
+    const long long od = ((long long)y * p.dst_w + x) * C;
+
+    const T *src = (const T *)p.src;
+    T *dst = (T *)p.dst;
+
+    if constexpr (sizeof(T) == 1) {
+        const int w00 = (32 - ax) * (32 - ay) * 32, w01 = ax * (32 - ay) * 32;
+        const int w10 = (32 - ax) * ay * 32, w11 = ax * ay * 32;
+        int bconst[C];  // contribution of out-of-range taps (+ rounding), frame invariant
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int bv = border_u8(p.border[c]);
+            bconst[c] = 16384 + bv * ((in00 ? 0 : w00) + (in01 ? 0 : w01) + (in10 ? 0 : w10) +
+                                      (in11 ? 0 : w11));
+        }
+        const int v00 = in00 ? w00 : 0, v01 = in01 ? w01 : 0, v10 = in10 ? w10 : 0,
+                  v11 = in11 ? w11 : 0;
+        for (int f = f0; f < f1; ++f) {
+            const long long fr = (long long)(g.first + f * g.stride);
+            const uint8_t *s = (const uint8_t *)src + fr * p.src_frame_elems;
+            uint8_t *d = (uint8_t *)dst + fr * p.dst_frame_elems + od;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                int acc = bconst[c];
+                if (in00) acc += v00 * (int)__ldg(s + o00 + c);
+                if (in01) acc += v01 * (int)__ldg(s + o01 + c);
+                if (in10) acc += v10 * (int)__ldg(s + o10 + c);
+                if (in11) acc += v11 * (int)__ldg(s + o11 + c);
+                d[c] = (uint8_t)(acc >> 15);
+            }
+        }
+    } else {
+        // cv2's float path: weights in fp32, products summed left to right, never fused
+        const float tx = __fmul_rn((float)ax, 1.0f / 32.0f), ty = __fmul_rn((float)ay, 1.0f / 32.0f);
+        const float omx = __fsub_rn(1.0f, tx), omy = __fsub_rn(1.0f, ty);
+        const float w00 = __fmul_rn(omy, omx), w01 = __fmul_rn(omy, tx);
+        const float w10 = __fmul_rn(ty, omx), w11 = __fmul_rn(ty, tx);
+        for (int f = f0; f < f1; ++f) {
+            const long long fr = (long long)(g.first + f * g.stride);
+            const T *s = src + fr * p.src_frame_elems;
+            T *d = dst + fr * p.dst_frame_elems + od;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float bv = p.border[c];
+                const float p00 = in00 ? Px<T>::ld(s + o00 + c) : bv;
+                const float p01 = in01 ? Px<T>::ld(s + o01 + c) : bv;
+                const float p10 = in10 ? Px<T>::ld(s + o10 + c) : bv;
+                const float p11 = in11 ? Px<T>::ld(s + o11 + c) : bv;
+                float r = __fadd_rn(__fmul_rn(p00, w00), __fmul_rn(p01, w01));
+                r = __fadd_rn(r, __fmul_rn(p10, w10));
+                r = __fadd_rn(r, __fmul_rn(p11, w11));
+                if constexpr (sizeof(T) == 2)
+                    d[c] = __float2half_rn(r);
+                else
+                    d[c] = r;
+            }
+        }
+    }
+}
+
+// ---- nearest ----------------------------------------------------------------------------------
+template <typename T, int C>
+__global__ void __launch_bounds__(256) warp_nearest_kernel(const __grid_constant__ BevkWarpParams p)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= p.dst_w || y >= p.dst_h) return;
+    int gi;
+    const BevkWarpGroup &g = find_group(p, blockIdx.z, gi);
+    const int c_local = blockIdx.z - g.chunk0;
+    const int f0 = c_local * p.frames_per_chunk;
+    const int f1 = min(f0 + p.frames_per_chunk, g.count);
+
+    int X, Y;
+    bevk_map_pixel(g.M, x, y, p.bw0, 1.0, X, Y);
+    const int sx = bevk_sat16(X), sy = bevk_sat16(Y);
+    const bool inside = (sx >= 0 && sx < p.src_w && sy >= 0 && sy < p.src_h);
+    const long long os = ((long long)sy * p.src_w + sx) * C;
+    const long long od = ((long long)y * p.dst_w + x) * C;
+    const T *src = (const T *)p.src;
+    T *dst = (T *)p.dst;
+
+    T bv[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        if constexpr (sizeof(T) == 1)
+            bv[c] = border_u8(p.border[c]);
+        else if constexpr (sizeof(T) == 2)
+            bv[c] = __float2half_rn(p.border[c]);
+        else
+            bv[c] = p.border[c];
+    }
+    for (int f = f0; f < f1; ++f) {
+        const long long fr = (long long)(g.first + f * g.stride);
+        const T *s = src + fr * p.src_frame_elems + os;
+        T *d = dst + fr * p.dst_frame_elems + od;
+#pragma unroll
+        for (int c = 0; c < C; ++c) d[c] = inside ? __ldg(s + c) : bv[c];
+    }
+}
+
+template <typename T, int C>
+int launch_tc(const BevkWarpParams &p, int linear, cudaStream_t stream)
+{
+    dim3 block(32, 8, 1);
+    dim3 grid((p.dst_w + 31) / 32, (p.dst_h + 7) / 8, p.total_chunks);
+    if (linear)
+        warp_linear_kernel<T, C><<<grid, block, 0, stream>>>(p);
+    else
+        warp_nearest_kernel<T, C><<<grid, block, 0, stream>>>(p);
+    BEVK_CUDA(cudaGetLastError());
+    return BEVK_OK;
+}
+
+template <typename T>
+int launch_t(const BevkWarpParams &p, int channels, int linear, cudaStream_t stream)
+{
+    switch (channels) {
+    case 1: return launch_tc<T, 1>(p, linear, stream);
+    case 2: return launch_tc<T, 2>(p, linear, stream);
+    case 3: return launch_tc<T, 3>(p, linear, stream);
+    case 4: return launch_tc<T, 4>(p, linear, stream);
+    }
+    BEVK_FAIL(BEVK_E_ARG, "channels must be 1..4, got %d", channels);
+}
+
+}  // namespace
+
+int bevk_launch_warp_generic(const BevkWarpParams &p, int channels, int dtype, int linear,
+                             cudaStream_t stream)
+{
+    switch (dtype) {
+    case BEVK_U8: return launch_t<uint8_t>(p, channels, linear, stream);
+    case BEVK_F16: return launch_t<__half>(p, channels, linear, stream);
+    case BEVK_F32: return launch_t<float>(p, channels, linear, stream);
+    }
+    BEVK_FAIL(BEVK_E_ARG, "warp dtype must be BEVK_U8/F16/F32, got %d", dtype);
+}
+
+// ---- touched-pixel accounting -----------------------------------------------------------------
+namespace {
+__global__ void footprint_mark_kernel(uint8_t *mask, int src_h, int src_w, int dst_h, int dst_w,
+                                      BevkWarpGroup g, int bw0, int linear, int *rows)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= dst_w || y >= dst_h) return;
+    int X, Y;
+    bevk_map_pixel(g.M, x, y, bw0, linear ? 32.0 : 1.0, X, Y);
+    const int sx = bevk_sat16(linear ? (X >> 5) : X), sy = bevk_sat16(linear ? (Y >> 5) : Y);
+    const int nt = linear ? 2 : 1;
+    for (int j = 0; j < nt; ++j)
+        for (int i = 0; i < nt; ++i) {
+            const int u = sx + i, v = sy + j;
+            if (u >= 0 && u < src_w && v >= 0 && v < src_h) {
+                mask[(size_t)v * src_w + u] = 1;
+                atomicMin(&rows[0], v);
+                atomicMax(&rows[1], v);
+            }
+        }
+}
+__global__ void footprint_count_kernel(const uint8_t *mask, size_t n, unsigned long long *count)
+{
+    unsigned long long local = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x)
+        local += mask[i];
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, local);
+}
+}  // namespace
+
+extern "C" int64_t bevk_warp_touched_pixels(int src_h, int src_w, int dst_h, int dst_w,
+                                            const double M[9], int flags, int *row_range)
+{
+    int rc = bevk_require_device();
+    if (rc) return rc;
+    if (!M || src_h <= 0 || src_w <= 0 || dst_h <= 0 || dst_w <= 0)
+        BEVK_FAIL(BEVK_E_ARG, "bevk_warp_touched_pixels: bad sizes / null matrix");
+    const int interp = flags & 7;
+    if (interp != BEVK_INTER_NEAREST && interp != BEVK_INTER_LINEAR)
+        BEVK_FAIL(BEVK_E_ARG, "unsupported interpolation flag %d", interp);
+    BevkWarpGroup g = {};
+    if (flags & BEVK_WARP_INVERSE_MAP)
+        for (int i = 0; i < 9; ++i) g.M[i] = M[i];
+    else
+        bevk_invert3x3(M, g.M);
+    uint8_t *mask = nullptr;
+    int *rows = nullptr;
+    unsigned long long *count = nullptr;
+    const size_t n = (size_t)src_h * src_w;
+    BEVK_CUDA(cudaMalloc(&mask, n));
+    BEVK_CUDA(cudaMalloc(&rows, 2 * sizeof(int)));
+    BEVK_CUDA(cudaMalloc(&count, sizeof(unsigned long long)));
+    const int init_rows[2] = {src_h, -1};
+    cudaMemset(mask, 0, n);
+    cudaMemset(count, 0, sizeof(unsigned long long));
+    cudaMemcpy(rows, init_rows, sizeof(init_rows), cudaMemcpyHostToDevice);
+    dim3 block(32, 8), grid((dst_w + 31) / 32, (dst_h + 7) / 8);
+    footprint_mark_kernel<<<grid, block>>>(mask, src_h, src_w, dst_h, dst_w, g,
+                                           bevk_block_width(dst_w, dst_h),
+                                           interp == BEVK_INTER_LINEAR, rows);
+    footprint_count_kernel<<<296, 256>>>(mask, n, count);
+    unsigned long long h_count = 0;
+    int h_rows[2] = {0, 0};
+    cudaError_t e = cudaMemcpy(&h_count, count, sizeof(h_count), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(h_rows, rows, sizeof(h_rows), cudaMemcpyDeviceToHost);
+    cudaFree(mask);
+    cudaFree(rows);
+    cudaFree(count);
+    if (e != cudaSuccess) BEVK_FAIL(BEVK_E_CUDA, "footprint kernels failed: %s", cudaGetErrorString(e));
+    if (row_range) {
+        row_range[0] = h_rows[0];
+        row_range[1] = h_rows[1];
+    }
+    return (int64_t)h_count;
+}

@@ -1,0 +1,103 @@
+"""Rotated-box and point projection on CUDA tensors.
+
+Same function names, argument order and return shapes as /root/reference/bev/rbox_torch.py (so
+``from bev_b200 import rbox_torch`` is a drop-in), plus the torch twins the reference only has in
+numpy (``pts_world_bev``, ``xy82xywhr``, ``rbox_world_img`` -- bev/rbox.py:136,50,221) and the two
+fused chains of BASELINE configs[2] (``xywhr_to_img_corners`` / ``img_corners_to_xywhr``).
+
+Each call is ONE CUDA kernel that reads every box once and writes it once (the reference issues
+~14-25 eager ATen ops with >= 10 temporaries per call).  Inputs must be float32/float64 CUDA
+tensors; homographies are host float64 3x3 (numpy or CPU tensor).  Coordinate conventions
+(reference rbox_torch.py:12-22):
+
+  bev   : u right, v down; yaw 0 = +v, yaw = atan2(u, v); w along u, h along v
+  world : right-handed x/y; yaw 0 = +x, yaw = atan2(y, x); h along x, w along y
+"""
+from . import _native
+
+_MODES = ("bev", "world")
+
+
+def _mode(mode):
+    assert mode in _MODES  # same AssertionError as the reference for a bad mode string
+    return _native.MODE[mode]
+
+
+def v2yaw(x, mode):
+    """(N,2) direction vectors -> (N,) yaw (reference rbox_torch.py:24-31)."""
+    return _native.rows_op("bevk_v2yaw", x, 2, (), _mode(mode))
+
+
+def yaw2v(x, mode):
+    """(N,) yaw -> (N,2) unit vectors (reference rbox_torch.py:33-40)."""
+    return _native.rows_op("bevk_yaw2v", x, 1, (2,), _mode(mode))
+
+
+def yaw2mat(x, mode):
+    """(N,) yaw -> (N,2,2) rotation matrices (reference rbox_torch.py:42-50)."""
+    return _native.rows_op("bevk_yaw2mat", x, 1, (2, 2), _mode(mode))
+
+
+def xywhr2xyxy(x, mode, external_aa=False):
+    """(N,5) [x,y,w,h,yaw] -> (N,8) corners tl,bl,br,tr (reference rbox_torch.py:52-99).
+
+    ``external_aa=True`` is dead code in the reference (it raises IndexError there, SURVEY.md
+    App. C) and is rejected here.
+    """
+    m = _mode(mode)
+    if external_aa:
+        raise NotImplementedError("external_aa=True is broken in the reference and not provided")
+    return _native.rows_op("bevk_xywhr2xyxy", x, 5, (8,), m, H=None, has_H=True)
+
+
+def xywhr2xyvec(xywhr, mode):
+    """(N,5) -> (N,4) heading segment [x, y, x + h*dx, y + h*dy] (reference rbox_torch.py:101-112)."""
+    return _native.rows_op("bevk_xywhr2xyvec", xywhr, 5, (4,), _mode(mode))
+
+
+def xy82xyvec(xy8):
+    """(N,8) corners -> (N,4) heading segment (reference rbox_torch.py:114-121)."""
+    return _native.rows_op("bevk_xy82xyvec", xy8, 8, (4,))
+
+
+def rbox_world_bev(rbox_src, H, src):
+    """Similarity transform of (N,5) boxes between bev and world (reference rbox_torch.py:123-168).
+
+    ``H`` must be affine and a similarity, else AssertionError as in the reference -- checked on
+    the host copy of H before launch, so a CUDA tensor is never synchronised on.
+    """
+    return _native.rows_op("bevk_rbox_world_bev", rbox_src, 5, (5,), _mode(src), H=H, has_H=True)
+
+
+# ---- torch twins of numpy-only reference functions ---------------------------------------------
+
+def pts_world_bev(pts_src, H):
+    """Homogeneous projection with divide; (N,2)->(N,2) or (N,3)->(N,3) (reference rbox.py:136-151)."""
+    if pts_src.dim() == 1:
+        pts_src = pts_src[None, :]
+    dim = pts_src.shape[1]
+    assert dim in (2, 3)
+    return _native.rows_op("bevk_pts_project", pts_src, dim, (dim,), dim, H=H, has_H=True)
+
+
+def xy82xywhr(xy8, mode):
+    """(N,8) corners -> (N,5) [x,y,w,h,yaw] (reference rbox.py:50-63)."""
+    return _native.rows_op("bevk_xy82xywhr", xy8, 8, (5,), _mode(mode), H=None, has_H=True)
+
+
+def rbox_world_img(rbox_world, H_img_world):
+    """Box centres through a full homography (reference rbox.py:221-226)."""
+    return pts_world_bev(rbox_world[:, :2], H_img_world)
+
+
+# ---- fused chains (BASELINE configs[2]) ------------------------------------------------------------
+
+def xywhr_to_img_corners(xywhr, H, mode):
+    """xywhr2xyxy followed by perspective projection of the 4 corners, in one pass
+    (the chain of reference bev/visualizer/rbox_vis.py:38-55)."""
+    return _native.rows_op("bevk_xywhr2xyxy", xywhr, 5, (8,), _mode(mode), H=H, has_H=True)
+
+
+def img_corners_to_xywhr(xy8, H, mode):
+    """Project 4 corners with H, then xy82xywhr, in one pass (the way back of configs[2])."""
+    return _native.rows_op("bevk_xy82xywhr", xy8, 8, (5,), _mode(mode), H=H, has_H=True)

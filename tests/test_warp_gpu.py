@@ -1,0 +1,202 @@
+"""GPU parity: bev_b200.homo.warp_perspective (CUDA, through the C ABI) vs the oracle
+(oracle/warp_oracle.c, pinned to cv2 4.13) and the committed cv2 fixtures.
+
+Bars (BASELINE.json north_star / SURVEY.md 8c): nearest bit-exact; bilinear uint8 contract <= 1 LSB,
+asserted bit-exact here; float32 bit-exact; float16 == float16(oracle(float32(src)))."""
+import numpy as np
+import pytest
+import torch
+
+from bev_b200 import _native, homo
+from oracle import warp_oracle as wo
+from tests import util
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+PATHS = ["generic", "auto"]
+
+
+def gpu_warp(src_np, H, dsize, flags=1, bv=0, **kw):
+    t = torch.from_numpy(np.ascontiguousarray(src_np)).to(DEV)
+    out = homo.warp_perspective(t, H, dsize, flags=flags, borderValue=bv, **kw)
+    assert out.device.type == "cuda" and out.dtype == t.dtype
+    return out.cpu().numpy()
+
+
+@pytest.fixture(params=PATHS)
+def path(request):
+    _native.set_warp_path(request.param)
+    yield request.param
+    _native.set_warp_path("auto")
+
+
+def test_native_library_is_the_one_running():
+    sm, major, minor = _native.device_info()
+    assert major == 10 and sm >= 100
+
+
+def test_small_golden_fixtures(path):
+    for case in util.small_cases():
+        out = gpu_warp(case["src"], case["H"], (50, 37), case["flags"], case["bv"])
+        assert util.bits_equal(out, case["dst"]), (path, case["name"])
+
+
+@pytest.mark.parametrize("case", util.hash_cases(), ids=lambda c: c["name"])
+def test_full_size_vs_cv2_hash(case, path):
+    src = util.hash_case_input(case)
+    out = gpu_warp(src, np.array(case["H"]), case["dsize"], case["flags"])
+    assert util.sha256(out) == case["sha256"], path
+
+
+@pytest.mark.parametrize("dtype", ["uint8", "float16", "float32"])
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
+@pytest.mark.parametrize("flags", [0, 1, 16, 17])
+def test_dtype_channel_matrix_vs_oracle(dtype, ch, flags, path):
+    rng = np.random.default_rng(ch * 31 + flags)
+    src = util.seeded_frame(50 + ch, 135, 240, ch, dtype)
+    s = np.array([[0, 0], [239, 0], [239, 134], [0, 134]], np.float64) + rng.normal(size=(4, 2)) * 25
+    d = np.array([[0, 0], [159, 0], [159, 99], [0, 99]], np.float64) + rng.normal(size=(4, 2)) * 10
+    H = homo.homo_from_pts(s, d)
+    if flags & 16:
+        H = np.linalg.inv(H)
+    ref = wo.warp_perspective(src, H, (160, 100), flags=flags, borderValue=(3, 50, 100, 250))
+    out = gpu_warp(src, H, (160, 100), flags, (3, 50, 100, 250))
+    assert util.bits_equal(out, ref)
+
+
+def test_batch_one_matrix_matches_per_frame(path):
+    H = util.h_canon()
+    S = np.diag([0.25, 0.25, 1.0])
+    Hs = S @ H @ np.linalg.inv(S)  # canonical geometry at quarter size: 480x270 -> 256x256
+    frames = np.stack([util.seeded_frame(900 + i, 270, 480, 3, "uint8") for i in range(37)])
+    out = gpu_warp(frames, Hs, (256, 256), 1)
+    assert out.shape == (37, 256, 256, 3)
+    for i in (0, 1, 17, 36):
+        assert util.bits_equal(out[i], wo.warp_perspective(frames[i], Hs, (256, 256), 1)), i
+
+
+def test_many_matrices_one_call(path):
+    cams = util.load_json("cfg4_cams.json")
+    S = np.diag([0.25, 0.25, 1.0])
+    n = 24
+    frames = np.stack([util.seeded_frame(700 + i, 270, 480, 3, "uint8") for i in range(n)])
+    # all cameras rendered to one BEV size so they can share a batch
+    Hs = np.stack([np.diag([0.5, 0.5, 1.0]) @ np.array(c["H_bev_img"]) @ np.linalg.inv(S) for c in cams])
+    idx = np.array([(i * 5) % 8 for i in range(n)], np.int32)  # interleaved, not contiguous
+    out = gpu_warp(frames, Hs, (160, 320), 1, mat_index=idx)
+    for i in range(n):
+        assert util.bits_equal(out[i], wo.warp_perspective(frames[i], Hs[idx[i]], (160, 320), 1)), i
+    # one matrix per frame, no index
+    out2 = gpu_warp(frames[:8], Hs, (160, 320), 0)
+    for i in range(8):
+        assert util.bits_equal(out2[i], wo.warp_perspective(frames[i], Hs[i], (160, 320), 0)), i
+
+
+def test_round_trip_img_bev_img(path):
+    """Size-independent property at BASELINE size: warping a smooth image to BEV and back with the
+    inverse map reproduces it inside the BEV footprint (up to interpolation blur)."""
+    H = util.h_canon()
+    yy, xx = np.mgrid[0:1080, 0:1920]
+    img = ((xx * 0.05 + yy * 0.11) % 256).astype(np.uint8)
+    img = np.stack([img, 255 - img, (img // 2)], -1)
+    bev = gpu_warp(img, H, (1024, 1024), 1)
+    back = gpu_warp(bev, H, (1920, 1080), 1 | 16)
+    ref_bev = wo.warp_perspective(img, H, (1024, 1024), 1)
+    assert util.bits_equal(bev, ref_bev)
+    assert util.bits_equal(back, wo.warp_perspective(ref_bev, H, (1920, 1080), 17))
+
+
+def test_linearity_in_the_source(path):
+    """Bilinear uint8 is linear up to rounding: warp(a) + warp(b) is within 1 LSB of warp(a + b)."""
+    H = util.h_canon()
+    a = util.seeded_frame(1, 1080, 1920, 3, "uint8") // 2
+    b = util.seeded_frame(2, 1080, 1920, 3, "uint8") // 2
+    wa = gpu_warp(a, H, (1024, 1024), 1).astype(np.int32)
+    wb = gpu_warp(b, H, (1024, 1024), 1).astype(np.int32)
+    wab = gpu_warp(a + b, H, (1024, 1024), 1).astype(np.int32)
+    assert np.abs(wa + wb - wab).max() <= 1
+
+
+def test_identity_and_shift_are_copies(path):
+    src = util.seeded_frame(4, 300, 500, 3, "uint8")
+    for flags in (0, 1):
+        out = gpu_warp(src, np.eye(3), (500, 300), flags)
+        assert util.bits_equal(out, src)
+    T = np.array([[1.0, 0, 7], [0, 1.0, -3], [0, 0, 1.0]])
+    out = gpu_warp(src, T, (500, 300), 0)
+    assert util.bits_equal(out[:297, 7:], src[3:, :493])
+    assert not out[297:].any() and not out[:, :7].any()  # BORDER_CONSTANT 0
+
+
+def test_edge_shapes_and_empty(path):
+    H = np.array([[1.0, 0, 0.5], [0, 1.0, 0.5], [0, 0, 1.0]])
+    src = util.seeded_frame(1, 1, 1, 3, "uint8")
+    assert util.bits_equal(gpu_warp(src, H, (3, 2), 1), wo.warp_perspective(src, H, (3, 2), 1))
+    g = util.seeded_frame(2, 5, 7, 1, "uint8")[:, :, 0]
+    out = gpu_warp(g, H, (1, 1), 0)
+    assert out.shape == (1, 1) and util.bits_equal(out, wo.warp_perspective(g, H, (1, 1), 0))
+    empty = torch.zeros((0, 16, 16, 3), dtype=torch.uint8, device=DEV)
+    assert homo.warp_perspective(empty, np.eye(3), (8, 8)).shape == (0, 8, 8, 3)
+    # degenerate matrix: cv2 maps everything to the zero matrix inverse -> source (0,0) everywhere
+    src = util.seeded_frame(9, 20, 30, 3, "uint8")
+    Z = np.zeros((3, 3))
+    assert util.bits_equal(gpu_warp(src, Z, (16, 8), 1), wo.warp_perspective(src, Z, (16, 8), 1))
+    # horizon crossing inside the output (w changes sign)
+    Hh = np.array([[1.0, 0.2, -3.0], [0.1, 1.1, -2.0], [0.0, 0.03, -0.5]])
+    src = util.seeded_frame(10, 96, 128, 3, "uint8")
+    assert util.bits_equal(gpu_warp(src, Hh, (128, 96), 1), wo.warp_perspective(src, Hh, (128, 96), 1))
+
+
+def test_argument_validation():
+    t = torch.zeros(8, 8, 3, dtype=torch.uint8, device=DEV)
+    with pytest.raises(TypeError):
+        homo.warp_perspective(t.to(torch.int32), np.eye(3), (4, 4))
+    with pytest.raises(_native.NativeError):
+        homo.warp_perspective(t, np.eye(3), (4, 4), flags=2)       # INTER_CUBIC
+    with pytest.raises(_native.NativeError):
+        homo.warp_perspective(t, np.eye(3), (4, 4), borderMode=1)  # BORDER_REPLICATE
+    with pytest.raises(ValueError):
+        homo.warp_perspective(t, np.eye(4), (4, 4))
+    dst = torch.empty(4, 4, 3, dtype=torch.uint8, device=DEV)
+    assert homo.warp_perspective(t, np.eye(3), (4, 4), dst=dst) is dst
+
+
+def test_host_buffer_entry_point():
+    H = util.h_canon()
+    S = np.diag([0.25, 0.25, 1.0])
+    Hs = S @ H @ np.linalg.inv(S)
+    frames = np.stack([util.seeded_frame(300 + i, 270, 480, 3, "uint8") for i in range(19)])
+    out = _native.warp_perspective_host(frames, Hs, (256, 256), flags=1)
+    for i in (0, 9, 18):
+        assert util.bits_equal(out[i], wo.warp_perspective(frames[i], Hs, (256, 256), 1)), i
+    pinned = torch.from_numpy(frames).pin_memory()
+    dst = torch.empty((19, 256, 256, 3), dtype=torch.uint8).pin_memory()
+    _native.warp_perspective_host(pinned, Hs, (256, 256), dst=dst, flags=0)
+    assert util.bits_equal(dst.numpy()[5], wo.warp_perspective(frames[5], Hs, (256, 256), 0))
+    # horizon-crossing map uploads the whole frame
+    Hh = np.array([[1.0, 0.2, -3.0], [0.1, 1.1, -2.0], [0.0, 0.003, -0.5]])
+    out = _native.warp_perspective_host(frames[:3], Hh, (200, 100), flags=1)
+    assert util.bits_equal(out[2], wo.warp_perspective(frames[2], Hh, (200, 100), 1))
+
+
+def test_touched_pixels_matches_oracle():
+    H = util.h_canon()
+    assert _native.warp_touched_pixels((1920, 1080), (1024, 1024), H, 1) == (971287, 420, 1058)
+    assert _native.warp_touched_pixels((1920, 1080), (1024, 1024), H, 0) == \
+        wo.touched_pixels((1920, 1080), (1024, 1024), H, 0)
+
+
+def test_calibration_object_wrappers():
+    from bev_b200 import BEVWorldSpec, Calib
+    cam = util.load_json("cfg4_cams.json")[3]
+    c = Calib(vp1=np.array(cam["vp1"]), vp2=np.array(cam["vp2"]), height=cam["height"],
+              u_size=1920, v_size=1080)
+    spec = {k: v for k, v in cam["bspec"].items() if v is not None and k not in ("x_max", "y_max")}
+    b = BEVWorldSpec(**spec)
+    frames = torch.from_numpy(np.stack([util.seeded_frame(1234 + 3, 1080, 1920, 3, "uint8")] * 2)).to(DEV)
+    bev = homo.warp_img_to_bev(frames, c, b)
+    assert tuple(bev.shape) == (2, b.v_size, b.u_size, 3)
+    case = [h for h in util.hash_cases() if h["name"] == "cfg4_cam3_lin"][0]
+    assert util.sha256(bev[0].cpu().numpy()) == case["sha256"]
+    img = homo.warp_bev_to_img(bev, c, b)
+    assert tuple(img.shape) == (2, 1080, 1920, 3)
