@@ -221,16 +221,19 @@ def ours(args, wl):
 
     # ---- e2e: same metric through the host-buffer C-ABI call, pinned host memory, H2D + D2H timed
     e2e_steps = max(1, min(args.e2e_steps, args.steps))
-    h_src = torch.empty(frames.shape, dtype=tdtype).pin_memory()
-    h_src.copy_(frames)
-    h_dst = torch.empty(out.shape, dtype=tdtype).pin_memory()
-    _native.warp_perspective_host(h_src, H, dsize, dst=h_dst, flags=flags)  # warm-up (allocs)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        _native.warp_perspective_host(h_src, H, dsize, dst=h_dst, flags=flags)
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if args.no_e2e:
+        e2e_s = float("nan")
+    else:
+        h_src = torch.empty(frames.shape, dtype=tdtype).pin_memory()
+        h_src.copy_(frames)
+        h_dst = torch.empty(out.shape, dtype=tdtype).pin_memory()
+        _native.warp_perspective_host(h_src, H, dsize, dst=h_dst, flags=flags)  # warm-up (allocs)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            _native.warp_perspective_host(h_src, H, dsize, dst=h_dst, flags=flags)
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -320,6 +323,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling aid: skip the host-buffer leg")
     args = ap.parse_args()
 
     if args.impl == "reference":

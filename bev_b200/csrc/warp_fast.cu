@@ -1,4 +1,497 @@
-// warp_fast.cu -- staged fast path (placeholder until the tiled kernel lands).
+// warp_fast.cu -- staged perspective warp for uint8 x 3 channels (the BASELINE hot path:
+// cv2.warpPerspective on BGR video frames, reference vis_homo.py:85-91), sm_100a.
+//
+// Work item = (homography group, 64x16 dst tile, chunk of frames).  A CTA of 256 threads owns
+// one item at a time; every thread owns 4 dst pixels of the tile:
+//
+//   1. set-up, once per item: the exact FP64 coordinate pipeline of cv2 (bevk_map_pixel) gives
+//      each pixel its 2x2 source window, and frame-invariant registers are derived from it -- the
+//      shared-memory address of the window, a PRMT selector and the 8-bit interpolation weights
+//      already laid out as dp4a operands.  Out-of-image taps get weight 0 and a clamped address,
+//      so the frame loop has no border branches.  A block reduction yields the tile's source
+//      bounding box.
+//   2. frame loop: a dedicated producer warp has the TMA unit fetch the bounding-box rows of the
+//      next frames (cp.async.bulk global->shared, one bulk copy per row, completion on an
+//      mbarrier) into a ring of up to 8 stages while the 8 consumer warps interpolate the current
+//      frame out of shared memory.  Interpolation is integer only: horizontal pass = dp4a on the raw
+//      RGB words, vertical pass = IMAD with weights pre-scaled so the result lands in byte 2;
+//      this reproduces cv2's (sum w*p + 2^14) >> 15 bit for bit (the two passes are exact
+//      integer re-association of the same sum).
+//   3. stores: 4 lanes' pixels (12 B) are packed into 3 words with one shuffle + PRMT and
+//      written as fully coalesced 96 B segments.
+//
+// HBM traffic per frame is the touched source footprint (bounding boxes overlap by a row/column
+// and are re-served by L2) plus the output, i.e. the algorithmic bytes of SURVEY.md 8d.
 #include "bevk_common.cuh"
 
-int bevk_launch_warp_fast(const BevkWarpParams &, int, int, int, cudaStream_t) { return 0; }
+namespace {
+
+constexpr int kTileW = 64, kTileH = 16, kThreads = 256;
+constexpr int kRingBytes = 96 * 1024;  // stage ring per CTA; two CTAs per SM
+constexpr int kStageSlack = 32;        // window words may run a few bytes past the last row
+constexpr int kSmemBytes = kRingBytes + 256;
+
+// ---- PTX wrappers (mbarrier + bulk async copy = the TMA path without a tensor map) -------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(dst),
+        "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    return __byte_perm(a, b, sel);
+}
+__device__ __forceinline__ void st_stream(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Stops the compiler from re-deriving a loop-invariant value inside the frame loop.
+__device__ __forceinline__ void keep(uint32_t &v) { asm volatile("" : "+r"(v)); }
+__device__ __forceinline__ void keep(long long &v) { asm volatile("" : "+l"(v)); }
+
+struct TileBox {
+    int bx0, bx1, by0, by1;  // inclusive source pixel bounds of all active windows
+};
+
+// Frame-invariant description of one dst pixel (bilinear).
+struct PixLin {
+    uint32_t addr;   // byte offset (4-aligned) of the word holding the first window byte
+    uint32_t addr1;  // the same one source row below
+    uint32_t selA;   // PRMT selector -> [c0(tap0), c0(tap1), c1(tap0), c1(tap1)]
+    uint32_t wA0;    // column weights on bytes 0,1 (channel 0)
+    uint32_t wA1;    // column weights on bytes 2,3 (channel 1)
+    uint32_t v0, v1, v2;  // channel-2 column weights placed on the raw words
+    uint32_t b0, b1;      // row weights * 64
+};
+struct PixNN {
+    uint32_t addr;
+    uint32_t sel;   // PRMT selector -> [c0, c1, c2, 0]
+    uint32_t mask;  // 0x00ffffff when the tap is inside the image, else 0
+};
+
+__device__ __forceinline__ int find_group_item(const BevkWarpParams &p, int item)
+{
+    int gi = 0;
+#pragma unroll 1
+    for (int i = 1; i < p.n_groups; ++i)
+        if (item >= p.g[i].chunk0) gi = i;
+    return gi;
+}
+
+// 2-tap window along one axis: first index (clamped into the image) and the weight each of the
+// two window positions receives.  Taps outside [0, n) contribute nothing (border value 0).
+__device__ __forceinline__ void window(int s, int frac, int n, int &first, int &w0, int &w1)
+{
+    first = min(max(s, 0), n - 2);
+    const int t0 = 32 - frac, t1 = frac;  // weights of taps s and s+1
+    w0 = (first == s ? t0 : 0) + (first == s + 1 ? t1 : 0);
+    w1 = (first + 1 == s ? t0 : 0) + (first + 1 == s + 1 ? t1 : 0);
+}
+
+// Kernel layout: 8 consumer warps (256 threads, 4 dst pixels each) + 1 producer warp that only
+// drives the TMA.  Stages form a ring in shared memory whose depth adapts to the tile's source
+// footprint (small boxes -> up to 8 frames in flight, which is what hides HBM latency; a box
+// that needs a whole stage buffer still gets 2).  full[s] / empty[s] mbarriers connect the two
+// roles; there is no CTA-wide barrier inside the frame loop.
+constexpr int kMaxStages = 8;
+constexpr int kConsumerWarps = kThreads / 32;
+
+template <bool LINEAR>
+__global__ void __launch_bounds__(kThreads + 32, 2)
+warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p, const int tiles_x, const int tiles_y,
+                      const int total_items)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kRingBytes);  // full[8], empty[8]
+    __shared__ int s_box[4];
+    __shared__ int s_any;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool is_producer = warp == kConsumerWarps;
+    const uint32_t ring = smem_u32(smem);
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kMaxStages]);
+    if (tid == 0) {
+        for (int i = 0; i < kMaxStages; ++i) {
+            mbar_init(full0 + 8 * i, 1);
+            mbar_init(empty0 + 8 * i, kConsumerWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t uses = 0;  // bit s = parity of the number of times slot s has been used so far
+
+    const int n_tiles = tiles_x * tiles_y;
+    const uint8_t *src = (const uint8_t *)p.src;
+    uint8_t *dst = (uint8_t *)p.dst;
+    const int src_row_bytes = p.src_w * 3;
+
+#pragma unroll 1
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int gi = find_group_item(p, item);
+        const int g_first = p.g[gi].first, g_stride = p.g[gi].stride, g_count = p.g[gi].count;
+        const int local = item - p.g[gi].chunk0;
+        const int chunk = local / n_tiles, tile = local - chunk * n_tiles;
+        const int tile_y = tile / tiles_x, tile_x = tile - tile_y * tiles_x;
+        const int f0 = chunk * p.frames_per_chunk;
+        const int f1 = min(f0 + p.frames_per_chunk, g_count);
+
+        // ---- 1. set-up ------------------------------------------------------------------------
+        // consumer pixel k: row = 2*warp + (k >> 1), column = lane + 32 * (k & 1)
+        if (tid == 0) {
+            s_box[0] = 1 << 30;
+            s_box[1] = -1;
+            s_box[2] = 1 << 30;
+            s_box[3] = -1;
+            s_any = 0;
+        }
+        __syncthreads();
+
+        int cs[4], rs[4], wc0[4], wc1[4], wr0[4], wr1[4];
+        int bx0 = 1 << 30, bx1 = -1, by0 = 1 << 30, by1 = -1;
+        if (!is_producer) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int x = tile_x * kTileW + lane + 32 * (k & 1);
+                const int y = tile_y * kTileH + 2 * warp + (k >> 1);
+                const bool in_dst = (x < p.dst_w) && (y < p.dst_h);
+                int X, Y;
+                bevk_map_pixel(p.g[gi].M, min(x, p.dst_w - 1), min(y, p.dst_h - 1), p.bw0,
+                               LINEAR ? 32.0 : 1.0, X, Y);
+                if (LINEAR) {
+                    const int sx = bevk_sat16(X >> 5), sy = bevk_sat16(Y >> 5);
+                    window(sx, X & 31, p.src_w, cs[k], wc0[k], wc1[k]);
+                    window(sy, Y & 31, p.src_h, rs[k], wr0[k], wr1[k]);
+                } else {
+                    const int sx = bevk_sat16(X), sy = bevk_sat16(Y);
+                    const bool in = sx >= 0 && sx < p.src_w && sy >= 0 && sy < p.src_h;
+                    cs[k] = min(max(sx, 0), p.src_w - 1);
+                    rs[k] = min(max(sy, 0), p.src_h - 1);
+                    wc0[k] = in ? 1 : 0;
+                    wc1[k] = 0;
+                    wr0[k] = in ? 1 : 0;
+                    wr1[k] = 0;
+                }
+                const bool active = in_dst && (wc0[k] | wc1[k]) != 0 && (wr0[k] | wr1[k]) != 0;
+                if (!active) {
+                    wc0[k] = wc1[k] = wr0[k] = wr1[k] = 0;
+                } else {
+                    bx0 = min(bx0, cs[k]);
+                    bx1 = max(bx1, cs[k] + (LINEAR ? 1 : 0));
+                    by0 = min(by0, rs[k]);
+                    by1 = max(by1, rs[k] + (LINEAR ? 1 : 0));
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                bx0 = min(bx0, __shfl_xor_sync(0xffffffffu, bx0, o));
+                bx1 = max(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
+                by0 = min(by0, __shfl_xor_sync(0xffffffffu, by0, o));
+                by1 = max(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+            }
+            if (lane == 0 && bx1 >= 0) {
+                atomicMin(&s_box[0], bx0);
+                atomicMax(&s_box[1], bx1);
+                atomicMin(&s_box[2], by0);
+                atomicMax(&s_box[3], by1);
+                s_any = 1;
+            }
+        }
+        __syncthreads();
+        const bool any = s_any != 0;
+        bx0 = s_box[0];
+        bx1 = s_box[1];
+        by0 = s_box[2];
+        by1 = s_box[3];
+        __syncthreads();  // s_box / s_any are re-initialised by the next item
+
+        const int a0 = (3 * bx0) & ~15;
+        const int a1 = min((3 * (bx1 + 1) + 15) & ~15, src_row_bytes);
+        const int pitch = a1 - a0;
+        const int nrows = by1 - by0 + 1;
+        const int stage_stride = (pitch * nrows + kStageSlack + 127) & ~127;
+        const bool staged = any && stage_stride <= kRingBytes / 2;
+        const int n_stages = staged ? min(kMaxStages, kRingBytes / stage_stride) : 0;
+
+        if (is_producer) {
+            // ---- 2a. producer warp: keep the ring full ----------------------------------------
+            if (staged) {
+                const uint32_t bytes = (uint32_t)(pitch * nrows);
+                int slot = 0;
+#pragma unroll 1
+                for (int f = f0; f < f1; ++f) {
+                    const uint32_t fb = full0 + 8 * slot, eb = empty0 + 8 * slot;
+                    // k-th use of a slot waits for the (k-1)-th release; the first passes at once
+                    mbar_wait(eb, ((uses >> slot) & 1) ^ 1);
+                    uses ^= 1u << slot;
+                    const uint8_t *s = src + (long long)(g_first + f * g_stride) * p.src_frame_elems +
+                                       (long long)by0 * src_row_bytes + a0;
+                    if (lane == 0) mbar_expect_tx(fb, bytes);
+                    __syncwarp();
+                    const uint32_t sdst = ring + slot * stage_stride;
+                    for (int r = lane; r < nrows; r += 32)
+                        bulk_g2s(sdst + r * pitch, s + (long long)r * src_row_bytes, (uint32_t)pitch, fb);
+                    slot = (slot + 1 == n_stages) ? 0 : slot + 1;
+                }
+            }
+            continue;
+        }
+
+        // ---- consumers ----------------------------------------------------------------------------
+        // dst byte offsets (inside a frame) of the four 32-pixel segments this thread helps to
+        // store: lanes 4q..4q+2 write words 3q..3q+2 of a 96-byte segment
+        const int q = lane >> 2, r4 = lane & 3;
+        const uint32_t sel_pack = r4 == 0 ? 0x4210u : (r4 == 1 ? 0x5421u : 0x6542u);
+        bool seg_store[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int xs = tile_x * kTileW + 32 * (k & 1);
+            const int y = tile_y * kTileH + 2 * warp + (k >> 1);
+            const int valid_px = min(32, p.dst_w - xs);  // multiple of 4 (dst_w % 4 == 0)
+            seg_store[k] = (y < p.dst_h) && (r4 < 3) && (4 * q < valid_px);
+        }
+        // word this lane writes in the left segment of tile row 2*warp; the right segment is
+        // 96 bytes further, the next tile row one dst row further
+        long long d_step = (long long)g_stride * p.dst_frame_elems;
+        keep(d_step);
+        const long long row_step = (long long)p.dst_w * 3;
+        uint8_t *d = dst + (long long)(g_first + f0 * g_stride) * p.dst_frame_elems +
+                     ((long long)(tile_y * kTileH + 2 * warp) * p.dst_w + tile_x * kTileW) * 3 +
+                     (3 * q + r4) * 4;
+        auto store4 = [&](const uint32_t(&word)[4]) {
+            if (seg_store[0]) st_stream(reinterpret_cast<uint32_t *>(d), word[0]);
+            if (seg_store[1]) st_stream(reinterpret_cast<uint32_t *>(d + 96), word[1]);
+            if (seg_store[2]) st_stream(reinterpret_cast<uint32_t *>(d + row_step), word[2]);
+            if (seg_store[3]) st_stream(reinterpret_cast<uint32_t *>(d + row_step + 96), word[3]);
+        };
+
+        if (!any) {
+            // whole tile maps outside the source: constant border (0) for every frame
+#pragma unroll 1
+            for (int f = f0; f < f1; ++f, d += d_step) {
+                const uint32_t zero[4] = {0u, 0u, 0u, 0u};
+                store4(zero);
+            }
+        } else if (staged) {
+            // frame-invariant per-pixel registers
+            PixLin pl[4];
+            PixNN pn[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const bool act = (wc0[k] | wc1[k]) != 0;
+                const int A = act ? (rs[k] - by0) * pitch + 3 * cs[k] - a0 : 0;
+                const uint32_t o = A & 3;
+                if (LINEAR) {
+                    pl[k].addr = A & ~3;
+                    pl[k].selA = o | ((o + 3) << 4) | ((o + 1) << 8) | ((o + 4) << 12);
+                    pl[k].wA0 = wc0[k] | (wc1[k] << 8);
+                    pl[k].wA1 = pl[k].wA0 << 16;
+                    // channel 2 lives at window bytes o+2 (tap 0) and o+5 (tap 1)
+                    const uint32_t p2 = o + 2, p5 = o + 5;
+                    const uint32_t e2 = (uint32_t)wc0[k] << (8 * (p2 & 3));
+                    const uint32_t e5 = (uint32_t)wc1[k] << (8 * (p5 & 3));
+                    pl[k].v0 = (p2 < 4 ? e2 : 0u);
+                    pl[k].v1 = (p2 >= 4 ? e2 : 0u) | (p5 < 8 ? e5 : 0u);
+                    pl[k].v2 = (p5 >= 8 ? e5 : 0u);
+                    pl[k].b0 = wr0[k] * 64;
+                    pl[k].b1 = wr1[k] * 64;
+                    pl[k].addr1 = pl[k].addr + pitch;
+                    keep(pl[k].addr);
+                    keep(pl[k].addr1);
+                    keep(pl[k].wA1);
+                    keep(pl[k].b0);
+                    keep(pl[k].b1);
+                } else {
+                    pn[k].addr = A & ~3;
+                    pn[k].sel = o | ((o + 1) << 4) | ((o + 2) << 8) | (4u << 12);  // byte 3 is masked off
+                    pn[k].mask = act ? 0x00ffffffu : 0u;
+                }
+            }
+
+            int slot = 0;
+#pragma unroll 1
+            for (int f = f0; f < f1; ++f, d += d_step) {
+                mbar_wait(full0 + 8 * slot, (uses >> slot) & 1);
+                uses ^= 1u << slot;
+                const uint32_t sb = ring + slot * stage_stride;
+
+                uint32_t P[4];
+                if (LINEAR) {
+                    uint32_t w[4][6];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        w[k][0] = lds32(sb + pl[k].addr);
+                        w[k][1] = lds32(sb + pl[k].addr + 4);
+                        w[k][2] = lds32(sb + pl[k].addr + 8);
+                        w[k][3] = lds32(sb + pl[k].addr1);
+                        w[k][4] = lds32(sb + pl[k].addr1 + 4);
+                        w[k][5] = lds32(sb + pl[k].addr1 + 8);
+                    }
+                    // all shared-memory reads of this stage are done: hand the slot back early
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty0 + 8 * slot);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t ya0 = prmt(w[k][0], w[k][1], pl[k].selA);
+                        const uint32_t ya1 = prmt(w[k][3], w[k][4], pl[k].selA);
+                        // horizontal pass: h[row][channel] = sum over the two taps of a_i * p
+                        const uint32_t h00 = __dp4a(ya0, pl[k].wA0, 0u);
+                        const uint32_t h01 = __dp4a(ya0, pl[k].wA1, 0u);
+                        const uint32_t h10 = __dp4a(ya1, pl[k].wA0, 0u);
+                        const uint32_t h11 = __dp4a(ya1, pl[k].wA1, 0u);
+                        uint32_t h02 = __dp4a(w[k][0], pl[k].v0, 0u);
+                        h02 = __dp4a(w[k][1], pl[k].v1, h02);
+                        h02 = __dp4a(w[k][2], pl[k].v2, h02);
+                        uint32_t h12 = __dp4a(w[k][3], pl[k].v0, 0u);
+                        h12 = __dp4a(w[k][4], pl[k].v1, h12);
+                        h12 = __dp4a(w[k][5], pl[k].v2, h12);
+                        // vertical pass, scaled by 64: byte 2 of t is (sum w*p + 2^14) >> 15
+                        const uint32_t t0 = pl[k].b1 * h10 + (pl[k].b0 * h00 + 32768u);
+                        const uint32_t t1 = pl[k].b1 * h11 + (pl[k].b0 * h01 + 32768u);
+                        const uint32_t t2 = pl[k].b1 * h12 + (pl[k].b0 * h02 + 32768u);
+                        P[k] = prmt(prmt(t0, t1, 0x4462u), t2, 0x7610u);  // [c0, c1, c2, 0]
+                    }
+                } else {
+                    uint32_t w[4][2];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t a = sb + pn[k].addr;
+                        w[k][0] = lds32(a);
+                        w[k][1] = lds32(a + 4);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty0 + 8 * slot);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) P[k] = prmt(w[k][0], w[k][1], pn[k].sel) & pn[k].mask;
+                }
+                // pack 4 lanes x 3 bytes into 3 words and store 96-byte segments
+                uint32_t word[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    word[k] = prmt(P[k], __shfl_down_sync(0xffffffffu, P[k], 1), sel_pack);
+                store4(word);
+                slot = (slot + 1 == n_stages) ? 0 : slot + 1;
+            }
+        } else {
+            // bounding box larger than half the ring (extreme minification): same arithmetic
+            // straight from global memory
+            const uint8_t *s = src + (long long)(g_first + f0 * g_stride) * p.src_frame_elems;
+            const long long s_step = (long long)g_stride * p.src_frame_elems;
+#pragma unroll 1
+            for (int f = f0; f < f1; ++f, d += d_step, s += s_step) {
+                uint32_t P[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint8_t *t = s + (long long)rs[k] * src_row_bytes + 3 * cs[k];
+                    uint32_t px = 0;
+                    if (LINEAR) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const int h0 = wc0[k] * __ldg(t + c) + wc1[k] * __ldg(t + 3 + c);
+                            const int h1 = wc0[k] * __ldg(t + src_row_bytes + c) +
+                                           wc1[k] * __ldg(t + src_row_bytes + 3 + c);
+                            const uint32_t v = (uint32_t)(wr0[k] * h0 + wr1[k] * h1 + 512) >> 10;
+                            px |= v << (8 * c);
+                        }
+                    } else if (wc0[k]) {
+                        px = __ldg(t) | (__ldg(t + 1) << 8) | (__ldg(t + 2) << 16);
+                    }
+                    P[k] = px;
+                }
+                uint32_t word[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    word[k] = prmt(P[k], __shfl_down_sync(0xffffffffu, P[k], 1), sel_pack);
+                store4(word);
+            }
+        }
+    }
+}
+
+}  // namespace
+
+int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, int linear,
+                          cudaStream_t stream)
+{
+    // qualification: uint8 x 3, zero border, rows that the bulk copy / word stores can address
+    if (dtype != BEVK_U8 || channels != 3) return 0;
+    if (p_in.border[0] != 0.f || p_in.border[1] != 0.f || p_in.border[2] != 0.f) return 0;
+    if (p_in.src_w < 2 || p_in.src_h < 2) return 0;
+    if ((p_in.src_w * 3) % 16 != 0 || (p_in.dst_w % 4) != 0) return 0;
+    if (((uintptr_t)p_in.src % 16) != 0 || ((uintptr_t)p_in.dst % 4) != 0) return 0;
+
+    static bool attr_set[2] = {false, false};
+    auto kern = linear ? warp_fast_u8c3_kernel<true> : warp_fast_u8c3_kernel<false>;
+    if (!attr_set[linear ? 1 : 0]) {
+        BEVK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        attr_set[linear ? 1 : 0] = true;
+    }
+
+    BevkWarpParams p = p_in;
+    const int tiles_x = (p.dst_w + kTileW - 1) / kTileW, tiles_y = (p.dst_h + kTileH - 1) / kTileH;
+    const long long n_tiles = (long long)tiles_x * tiles_y;
+    const int ctas = bevk_sm_count() * 2;
+    int max_count = 0;
+    for (int i = 0; i < p.n_groups; ++i) max_count = max_count > p.g[i].count ? max_count : p.g[i].count;
+    // frames per chunk: as many as possible (amortises the FP64 set-up) while keeping at least
+    // ~4 items per resident CTA for balance
+    int fpc = max_count < 64 ? max_count : 64;
+    while (fpc > 8) {
+        long long items = 0;
+        for (int i = 0; i < p.n_groups; ++i) items += n_tiles * ((p.g[i].count + fpc - 1) / fpc);
+        if (items >= 4LL * ctas) break;
+        fpc = (fpc + 1) / 2;
+    }
+    p.frames_per_chunk = fpc;
+    long long items = 0;
+    for (int i = 0; i < p.n_groups; ++i) {
+        p.g[i].chunk0 = (int)items;
+        items += n_tiles * ((p.g[i].count + fpc - 1) / fpc);
+    }
+    if (items > 0x7fffffffLL) return 0;
+    p.total_chunks = (int)items;
+    const int grid = (int)(items < ctas ? items : ctas);
+    kern<<<grid, kThreads + 32, kSmemBytes, stream>>>(p, tiles_x, tiles_y, (int)items);
+    BEVK_CUDA(cudaGetLastError());
+    return 1;
+}
