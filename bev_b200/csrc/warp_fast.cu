@@ -1,37 +1,58 @@
 // warp_fast.cu -- staged perspective warp for uint8 x 3 channels (the BASELINE hot path:
 // cv2.warpPerspective on BGR video frames, reference vis_homo.py:85-91), sm_100a.
 //
-// Work item = (homography group, 64x16 dst tile, chunk of frames).  A CTA of 256 threads owns
-// one item at a time; every thread owns 4 dst pixels of the tile:
+// Work item = (homography group, 128x8 dst tile, chunk of frames).  A CTA of 8 warps owns one
+// item at a time; warp w owns tile row w, every thread owns 4 dst pixels of that row
+// (x = lane + 32k):
 //
 //   1. set-up, once per item: the exact FP64 coordinate pipeline of cv2 (bevk_map_pixel) gives
 //      each pixel its 2x2 source window, and frame-invariant registers are derived from it -- the
-//      shared-memory address of the window, a PRMT selector and the 8-bit interpolation weights
-//      already laid out as dp4a operands.  Out-of-image taps get weight 0 and a clamped address,
-//      so the frame loop has no border branches.  A block reduction yields the tile's source
-//      bounding box.
-//   2. frame loop: a dedicated producer warp has the TMA unit fetch the bounding-box rows of the
-//      next frames (cp.async.bulk global->shared, one bulk copy per row, completion on an
-//      mbarrier) into a ring of up to 8 stages while the 8 consumer warps interpolate the current
-//      frame out of shared memory.  Interpolation is integer only: horizontal pass = dp4a on the raw
-//      RGB words, vertical pass = IMAD with weights pre-scaled so the result lands in byte 2;
-//      this reproduces cv2's (sum w*p + 2^14) >> 15 bit for bit (the two passes are exact
-//      integer re-association of the same sum).
+//      shared-memory offset of the window, a funnel-shift amount that byte-aligns it and the
+//      8-bit interpolation weights already laid out as dp4a / dp2a operands.  Out-of-image taps
+//      get weight 0 and a clamped address, so the frame loop has no border branches.  A block
+//      reduction yields the tile's source bounding box.
+//   2. frame loop: the bounding box of the next frames is fetched by the TMA unit as 2-D tensor
+//      boxes (cp.async.bulk.tensor.2d, at most 3 requests per frame and tile, completion on an
+//      mbarrier) into a 2- or 4-deep shared-memory ring while the warps interpolate the current
+//      frame out of shared memory.  One elected thread issues the copies; full[] / empty[]
+//      mbarriers are the only synchronisation in the loop.  The box shape is picked per tile from
+//      a menu of tensor maps over the source batch viewed as a [frames*rows][row_bytes/4] uint32
+//      matrix (widths 64..1024 B, heights 1..64 rows).  A first version issued one
+//      cp.async.bulk per source row: the TMA unit retired only one such ~300-byte request per
+//      ~70 cycles per SM, which capped the kernel at 33 % of the HBM roofline
+//      (profiles/r01_fast_v1_*).
+//      Interpolation is integer only and spread over both integer pipes: funnel shifts + PRMT
+//      (ALU pipe) align the window, dp4a / dp2a (FMA pipe) do the horizontal pass, IMAD with
+//      weights pre-scaled by 64 does the vertical pass so that the result lands in byte 2.  This
+//      reproduces cv2's (sum w*p + 2^14) >> 15 bit for bit (the two passes are an exact integer
+//      re-association of the same sum).
 //   3. stores: 4 lanes' pixels (12 B) are packed into 3 words with one shuffle + PRMT and
-//      written as fully coalesced 96 B segments.
+//      written as fully coalesced 96 B segments, 384 contiguous bytes per warp and frame.
 //
-// HBM traffic per frame is the touched source footprint (bounding boxes overlap by a row/column
-// and are re-served by L2) plus the output, i.e. the algorithmic bytes of SURVEY.md 8d.
+// HBM traffic per frame is the touched source footprint (bounding boxes overlap by a row /
+// column and are re-served by L2: tiles are walked column-major so that neighbours run
+// concurrently and near-/far-field tiles mix) plus the output, i.e. the algorithmic bytes of
+// SURVEY.md 8d.
 #include "bevk_common.cuh"
+
+#include <cuda.h>  // CUtensorMap + enums only; the encoder is fetched through the runtime
+#include <mutex>
+#include <string.h>
 
 namespace {
 
-constexpr int kTileW = 64, kTileH = 16, kThreads = 256;
-constexpr int kRingBytes = 96 * 1024;  // stage ring per CTA; two CTAs per SM
-constexpr int kStageSlack = 32;        // window words may run a few bytes past the last row
-constexpr int kSmemBytes = kRingBytes + 256;
+constexpr int kTileW = 128, kTileH = 8, kThreads = 256, kWarps = kThreads / 32;
+constexpr int kMapWStep = 64, kMapWCount = 16;  // box widths 64, 128, ..., 1024 bytes
+constexpr int kMapHCount = 7;                   // box heights 1, 2, 4, ..., 64 rows
+constexpr int kMaxBoxes = 3;
+constexpr int kBarBytes = 128;                  // 12 mbarriers
+constexpr int kTailSlack = 64;                  // window words may run a few bytes past a stage
 
-// ---- PTX wrappers (mbarrier + bulk async copy = the TMA path without a tensor map) -------------
+struct WarpFastMaps {
+    CUtensorMap m[kMapWCount * kMapHCount];
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -63,12 +84,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         "r"(parity)
         : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+// 2-D tensor box global -> shared, completion counted in bytes on an mbarrier (the TMA path)
+__device__ __forceinline__ void tma_box_g2s(uint32_t dst, const CUtensorMap *map, int x, int y,
+                                            uint32_t bar)
 {
     asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-            "r"(dst),
-        "l"(src), "r"(bytes), "r"(bar)
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y)
         : "memory");
 }
 __device__ __forceinline__ uint32_t lds32(uint32_t addr)
@@ -85,30 +108,8 @@ __device__ __forceinline__ void st_stream(uint32_t *p, uint32_t v)
 {
     asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-
 // Stops the compiler from re-deriving a loop-invariant value inside the frame loop.
 __device__ __forceinline__ void keep(uint32_t &v) { asm volatile("" : "+r"(v)); }
-__device__ __forceinline__ void keep(long long &v) { asm volatile("" : "+l"(v)); }
-
-struct TileBox {
-    int bx0, bx1, by0, by1;  // inclusive source pixel bounds of all active windows
-};
-
-// Frame-invariant description of one dst pixel (bilinear).
-struct PixLin {
-    uint32_t addr;   // byte offset (4-aligned) of the word holding the first window byte
-    uint32_t addr1;  // the same one source row below
-    uint32_t selA;   // PRMT selector -> [c0(tap0), c0(tap1), c1(tap0), c1(tap1)]
-    uint32_t wA0;    // column weights on bytes 0,1 (channel 0)
-    uint32_t wA1;    // column weights on bytes 2,3 (channel 1)
-    uint32_t v0, v1, v2;  // channel-2 column weights placed on the raw words
-    uint32_t b0, b1;      // row weights * 64
-};
-struct PixNN {
-    uint32_t addr;
-    uint32_t sel;   // PRMT selector -> [c0, c1, c2, 0]
-    uint32_t mask;  // 0x00ffffff when the tap is inside the image, else 0
-};
 
 __device__ __forceinline__ int find_group_item(const BevkWarpParams &p, int item)
 {
@@ -129,37 +130,162 @@ __device__ __forceinline__ void window(int s, int frac, int n, int &first, int &
     w1 = (first + 1 == s ? t0 : 0) + (first + 1 == s + 1 ? t1 : 0);
 }
 
-// Kernel layout: 8 consumer warps (256 threads, 4 dst pixels each) + 1 producer warp that only
-// drives the TMA.  Stages form a ring in shared memory whose depth adapts to the tile's source
-// footprint (small boxes -> up to 8 frames in flight, which is what hides HBM latency; a box
-// that needs a whole stage buffer still gets 2).  full[s] / empty[s] mbarriers connect the two
-// roles; there is no CTA-wide barrier inside the frame loop.
-constexpr int kMaxStages = 8;
-constexpr int kConsumerWarps = kThreads / 32;
+// What the elected producer thread needs to fetch one frame's bounding box.
+struct BoxPlan {
+    int n_boxes;
+    int x;                  // first column, in uint32 elements
+    int y0;                 // first source row of the box
+    uint32_t bytes;         // sum of the box sizes (the mbarrier's transaction count)
+    int map_idx[kMaxBoxes];
+    int row[kMaxBoxes];     // row offset of each box inside the stage
+};
+
+// Frame-invariant description of one dst pixel.
+struct Pix {
+    uint32_t addr;   // byte offset (4-aligned) inside a stage of the first window word, row 0
+    uint32_t sh;     // 8 * (window start & 3): funnel-shift amount that byte-aligns the window
+    uint32_t w03;    // bilinear: column weights as bytes 0 and 3 (dp4a with [B0 B1 B2 B3] -> ch. 0)
+                     // nearest : 0x00ffffff when the tap is inside the image, else 0
+    uint32_t w16;    // column weights as 16-bit halves (dp2a lo/hi with [B1 B4 B2 B5] -> ch. 1, 2)
+    uint32_t b0, b1; // row weights * 64
+};
+
+// One pixel out of its staged window: cv2's fixed-point bilinear, result [c0, c1, c2, 0].
+__device__ __forceinline__ uint32_t lerp_pixel(const Pix &q, uint32_t r0, uint32_t r1, uint32_t r2,
+                                               uint32_t s0, uint32_t s1, uint32_t s2)
+{
+    // byte-align the window of both rows: F = [B0 B1 B2 B3], G = [B1 B4 B2 B5]
+    const uint32_t f0 = __funnelshift_r(r0, r1, q.sh), f1 = __funnelshift_r(r1, r2, q.sh);
+    const uint32_t g0 = __funnelshift_r(s0, s1, q.sh), g1 = __funnelshift_r(s1, s2, q.sh);
+    const uint32_t fg = prmt(f0, f1, 0x5241u), gg = prmt(g0, g1, 0x5241u);
+    // horizontal pass: h[row][channel] = a0 * tap0 + a1 * tap1
+    const uint32_t h00 = __dp4a(f0, q.w03, 0u);
+    const uint32_t h01 = __dp2a_lo(q.w16, fg, 0u);
+    const uint32_t h02 = __dp2a_hi(q.w16, fg, 0u);
+    const uint32_t h10 = __dp4a(g0, q.w03, 0u);
+    const uint32_t h11 = __dp2a_lo(q.w16, gg, 0u);
+    const uint32_t h12 = __dp2a_hi(q.w16, gg, 0u);
+    // vertical pass, scaled by 64: byte 2 of t is (sum w*p + 2^14) >> 15
+    const uint32_t t0 = q.b1 * h10 + (q.b0 * h00 + 32768u);
+    const uint32_t t1 = q.b1 * h11 + (q.b0 * h01 + 32768u);
+    const uint32_t t2 = q.b1 * h12 + (q.b0 * h02 + 32768u);
+    return prmt(prmt(t0, t1, 0x4462u), t2, 0x7610u);
+}
+
+struct LoopCtx {
+    uint32_t ring, full0, empty0;  // shared-memory addresses of the ring / first barrier of the set
+    uint32_t slog;                 // log2(ring depth)
+    uint32_t stride;               // bytes per stage
+    uint32_t pitch;                // bytes per staged row
+    int n_frames;
+    int frame0, frame_step;        // source / dst frame index of loop iteration i = frame0 + i * step
+    int src_h;
+    const WarpFastMaps *maps;
+    const BoxPlan *plan;           // in shared memory
+};
+
+// Elected thread: start the copy of frame `i` of the item into its ring slot.  `use` is the
+// running count of stages this CTA has pushed through the barrier set.
+__device__ __forceinline__ void produce(const LoopCtx &c, int i, uint32_t use)
+{
+    const uint32_t slot = use & ((1u << c.slog) - 1u);
+    // k-th fill of a slot waits for the (k-1)-th release; the first passes at once
+    mbar_wait(c.empty0 + 8 * slot, ((use >> c.slog) & 1u) ^ 1u);
+    const uint32_t fb = c.full0 + 8 * slot;
+    mbar_expect_tx(fb, c.plan->bytes);
+    const int y = (c.frame0 + i * c.frame_step) * c.src_h + c.plan->y0;
+    const uint32_t sdst = c.ring + slot * c.stride;
+    const int nb = c.plan->n_boxes;
+#pragma unroll 1
+    for (int b = 0; b < nb; ++b)
+        tma_box_g2s(sdst + c.plan->row[b] * c.pitch, &c.maps->m[c.plan->map_idx[b]], c.plan->x,
+                    y + c.plan->row[b], fb);
+}
+
+// The frame loop of a staged item.  FULL: every pixel of the tile is inside the dst image.
+template <bool LINEAR, bool FULL>
+__device__ __forceinline__ uint32_t frame_loop(const LoopCtx &c, const Pix (&px)[4], uint32_t use,
+                                               uint8_t *d, const long long d_step,
+                                               const bool lane_st, const bool (&seg_ok)[4],
+                                               const uint32_t sel_pack)
+{
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t smask = (1u << c.slog) - 1u;
+    const int ahead = (int)smask;  // frames in flight besides the one being consumed
+    if (tid == 0)
+        for (int i = 0; i < ahead && i < c.n_frames; ++i) produce(c, i, use + i);
+
+#pragma unroll 1
+    for (int i = 0; i < c.n_frames; ++i, d += d_step) {
+        const uint32_t slot = use & smask;
+        mbar_wait(c.full0 + 8 * slot, (use >> c.slog) & 1u);
+        const uint32_t sa = c.ring + slot * c.stride;  // row 0 of the windows
+        const uint32_t sb = sa + c.pitch;              // row 1
+        uint32_t P[4];
+        if (LINEAR) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t a = px[k].addr + sa, b = px[k].addr + sb;
+                const uint32_t r0 = lds32(a), r1 = lds32(a + 4), r2 = lds32(a + 8);
+                const uint32_t s0 = lds32(b), s1 = lds32(b + 4), s2 = lds32(b + 8);
+                if (k == 3) {
+                    // all shared-memory reads of this stage are issued: hand the slot back early
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(c.empty0 + 8 * slot);
+                    if (tid == 0 && i + ahead < c.n_frames) produce(c, i + ahead, use + ahead);
+                }
+                P[k] = lerp_pixel(px[k], r0, r1, r2, s0, s1, s2);
+            }
+        } else {
+            uint32_t w[4][2];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                w[k][0] = lds32(px[k].addr + sa);
+                w[k][1] = lds32(px[k].addr + sa + 4);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(c.empty0 + 8 * slot);
+            if (tid == 0 && i + ahead < c.n_frames) produce(c, i + ahead, use + ahead);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                P[k] = __funnelshift_r(w[k][0], w[k][1], px[k].sh) & px[k].w03;
+        }
+        ++use;
+        // pack 4 lanes x 3 bytes into 3 words and store 96-byte segments
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t word = prmt(P[k], __shfl_down_sync(0xffffffffu, P[k], 1), sel_pack);
+            if (FULL ? lane_st : seg_ok[k]) st_stream(reinterpret_cast<uint32_t *>(d + 96 * k), word);
+        }
+    }
+    return use;
+}
 
 template <bool LINEAR>
-__global__ void __launch_bounds__(kThreads + 32, 2)
-warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p, const int tiles_x, const int tiles_y,
-                      const int total_items)
+__global__ void __launch_bounds__(kThreads, 4)
+warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
+                      const __grid_constant__ WarpFastMaps maps, const int tiles_x,
+                      const int tiles_y, const int total_items, const int ring_bytes)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kRingBytes);  // full[8], empty[8]
+    // barrier set A (ring depth 2): full[2], empty[2]; set B (depth 4): full[4], empty[4]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + ring_bytes);
     __shared__ int s_box[4];
     __shared__ int s_any;
+    __shared__ BoxPlan s_plan;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool is_producer = warp == kConsumerWarps;
     const uint32_t ring = smem_u32(smem);
-    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kMaxStages]);
+    const uint32_t bar0 = smem_u32(bars);
     if (tid == 0) {
-        for (int i = 0; i < kMaxStages; ++i) {
-            mbar_init(full0 + 8 * i, 1);
-            mbar_init(empty0 + 8 * i, kConsumerWarps);
+        for (int i = 0; i < 12; ++i) {
+            const bool is_full = (i < 2) || (i >= 4 && i < 8);
+            mbar_init(bar0 + 8 * i, is_full ? 1 : kWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    uint32_t uses = 0;  // bit s = parity of the number of times slot s has been used so far
+    uint32_t use_a = 0, use_b = 0;  // stages pushed through barrier set A / B so far
 
     const int n_tiles = tiles_x * tiles_y;
     const uint8_t *src = (const uint8_t *)p.src;
@@ -172,12 +298,14 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p, const int tiles_
         const int g_first = p.g[gi].first, g_stride = p.g[gi].stride, g_count = p.g[gi].count;
         const int local = item - p.g[gi].chunk0;
         const int chunk = local / n_tiles, tile = local - chunk * n_tiles;
-        const int tile_y = tile / tiles_x, tile_x = tile - tile_y * tiles_x;
+        // column-major walk: concurrently running CTAs cover whole tile columns, i.e. both the
+        // magnified far field (store-heavy) and the minified near field (load-heavy)
+        const int tile_x = tile / tiles_y, tile_y = tile - tile_x * tiles_y;
         const int f0 = chunk * p.frames_per_chunk;
-        const int f1 = min(f0 + p.frames_per_chunk, g_count);
+        const int n_frames = min(f0 + p.frames_per_chunk, g_count) - f0;
+        const int x0 = tile_x * kTileW, y = tile_y * kTileH + warp;
 
         // ---- 1. set-up ------------------------------------------------------------------------
-        // consumer pixel k: row = 2*warp + (k >> 1), column = lane + 32 * (k & 1)
         if (tid == 0) {
             s_box[0] = 1 << 30;
             s_box[1] = -1;
@@ -189,53 +317,50 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p, const int tiles_
 
         int cs[4], rs[4], wc0[4], wc1[4], wr0[4], wr1[4];
         int bx0 = 1 << 30, bx1 = -1, by0 = 1 << 30, by1 = -1;
-        if (!is_producer) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int x = tile_x * kTileW + lane + 32 * (k & 1);
-                const int y = tile_y * kTileH + 2 * warp + (k >> 1);
-                const bool in_dst = (x < p.dst_w) && (y < p.dst_h);
-                int X, Y;
-                bevk_map_pixel(p.g[gi].M, min(x, p.dst_w - 1), min(y, p.dst_h - 1), p.bw0,
-                               LINEAR ? 32.0 : 1.0, X, Y);
-                if (LINEAR) {
-                    const int sx = bevk_sat16(X >> 5), sy = bevk_sat16(Y >> 5);
-                    window(sx, X & 31, p.src_w, cs[k], wc0[k], wc1[k]);
-                    window(sy, Y & 31, p.src_h, rs[k], wr0[k], wr1[k]);
-                } else {
-                    const int sx = bevk_sat16(X), sy = bevk_sat16(Y);
-                    const bool in = sx >= 0 && sx < p.src_w && sy >= 0 && sy < p.src_h;
-                    cs[k] = min(max(sx, 0), p.src_w - 1);
-                    rs[k] = min(max(sy, 0), p.src_h - 1);
-                    wc0[k] = in ? 1 : 0;
-                    wc1[k] = 0;
-                    wr0[k] = in ? 1 : 0;
-                    wr1[k] = 0;
-                }
-                const bool active = in_dst && (wc0[k] | wc1[k]) != 0 && (wr0[k] | wr1[k]) != 0;
-                if (!active) {
-                    wc0[k] = wc1[k] = wr0[k] = wr1[k] = 0;
-                } else {
-                    bx0 = min(bx0, cs[k]);
-                    bx1 = max(bx1, cs[k] + (LINEAR ? 1 : 0));
-                    by0 = min(by0, rs[k]);
-                    by1 = max(by1, rs[k] + (LINEAR ? 1 : 0));
-                }
+        for (int k = 0; k < 4; ++k) {
+            const int x = x0 + lane + 32 * k;
+            const bool in_dst = (x < p.dst_w) && (y < p.dst_h);
+            int X, Y;
+            bevk_map_pixel(p.g[gi].M, min(x, p.dst_w - 1), min(y, p.dst_h - 1), p.bw0,
+                           LINEAR ? 32.0 : 1.0, X, Y);
+            if (LINEAR) {
+                const int sx = bevk_sat16(X >> 5), sy = bevk_sat16(Y >> 5);
+                window(sx, X & 31, p.src_w, cs[k], wc0[k], wc1[k]);
+                window(sy, Y & 31, p.src_h, rs[k], wr0[k], wr1[k]);
+            } else {
+                const int sx = bevk_sat16(X), sy = bevk_sat16(Y);
+                const bool in = sx >= 0 && sx < p.src_w && sy >= 0 && sy < p.src_h;
+                cs[k] = min(max(sx, 0), p.src_w - 1);
+                rs[k] = min(max(sy, 0), p.src_h - 1);
+                wc0[k] = in ? 1 : 0;
+                wc1[k] = 0;
+                wr0[k] = in ? 1 : 0;
+                wr1[k] = 0;
             }
+            const bool active = in_dst && (wc0[k] | wc1[k]) != 0 && (wr0[k] | wr1[k]) != 0;
+            if (!active) {
+                wc0[k] = wc1[k] = wr0[k] = wr1[k] = 0;
+            } else {
+                bx0 = min(bx0, cs[k]);
+                bx1 = max(bx1, cs[k] + (LINEAR ? 1 : 0));
+                by0 = min(by0, rs[k]);
+                by1 = max(by1, rs[k] + (LINEAR ? 1 : 0));
+            }
+        }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                bx0 = min(bx0, __shfl_xor_sync(0xffffffffu, bx0, o));
-                bx1 = max(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
-                by0 = min(by0, __shfl_xor_sync(0xffffffffu, by0, o));
-                by1 = max(by1, __shfl_xor_sync(0xffffffffu, by1, o));
-            }
-            if (lane == 0 && bx1 >= 0) {
-                atomicMin(&s_box[0], bx0);
-                atomicMax(&s_box[1], bx1);
-                atomicMin(&s_box[2], by0);
-                atomicMax(&s_box[3], by1);
-                s_any = 1;
-            }
+        for (int o = 16; o > 0; o >>= 1) {
+            bx0 = min(bx0, __shfl_xor_sync(0xffffffffu, bx0, o));
+            bx1 = max(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
+            by0 = min(by0, __shfl_xor_sync(0xffffffffu, by0, o));
+            by1 = max(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+        }
+        if (lane == 0 && bx1 >= 0) {
+            atomicMin(&s_box[0], bx0);
+            atomicMax(&s_box[1], bx1);
+            atomicMin(&s_box[2], by0);
+            atomicMax(&s_box[3], by1);
+            s_any = 1;
         }
         __syncthreads();
         const bool any = s_any != 0;
@@ -243,209 +368,246 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p, const int tiles_
         bx1 = s_box[1];
         by0 = s_box[2];
         by1 = s_box[3];
-        __syncthreads();  // s_box / s_any are re-initialised by the next item
 
+        // staged geometry: 16-byte aligned first column, width rounded to the tensor-map menu
         const int a0 = (3 * bx0) & ~15;
-        const int a1 = min((3 * (bx1 + 1) + 15) & ~15, src_row_bytes);
-        const int pitch = a1 - a0;
+        const int need_w = ((3 * (bx1 + 1) + 15) & ~15) - a0;
+        const int pitch = (need_w + kMapWStep - 1) / kMapWStep * kMapWStep;
         const int nrows = by1 - by0 + 1;
-        const int stage_stride = (pitch * nrows + kStageSlack + 127) & ~127;
-        const bool staged = any && stage_stride <= kRingBytes / 2;
-        const int n_stages = staged ? min(kMaxStages, kRingBytes / stage_stride) : 0;
-
-        if (is_producer) {
-            // ---- 2a. producer warp: keep the ring full ----------------------------------------
-            if (staged) {
-                const uint32_t bytes = (uint32_t)(pitch * nrows);
-                int slot = 0;
-#pragma unroll 1
-                for (int f = f0; f < f1; ++f) {
-                    const uint32_t fb = full0 + 8 * slot, eb = empty0 + 8 * slot;
-                    // k-th use of a slot waits for the (k-1)-th release; the first passes at once
-                    mbar_wait(eb, ((uses >> slot) & 1) ^ 1);
-                    uses ^= 1u << slot;
-                    const uint8_t *s = src + (long long)(g_first + f * g_stride) * p.src_frame_elems +
-                                       (long long)by0 * src_row_bytes + a0;
-                    if (lane == 0) mbar_expect_tx(fb, bytes);
-                    __syncwarp();
-                    const uint32_t sdst = ring + slot * stage_stride;
-                    for (int r = lane; r < nrows; r += 32)
-                        bulk_g2s(sdst + r * pitch, s + (long long)r * src_row_bytes, (uint32_t)pitch, fb);
-                    slot = (slot + 1 == n_stages) ? 0 : slot + 1;
+        bool staged = any && pitch <= kMapWStep * kMapWCount && nrows <= 128;
+        if (tid == 0 && staged) {
+            // cover the rows with at most kMaxBoxes boxes of power-of-two height, largest first
+            int rem = nrows, row = 0, nb = 0;
+            while (rem > 0) {
+                int h = 1 << (31 - __clz(rem));
+                const int up = (h == rem) ? h : 2 * h;
+                if (nb == kMaxBoxes - 1 || up - rem <= max(1, rem >> 3)) h = up;
+                h = min(h, 1 << (kMapHCount - 1));
+                if (nb == kMaxBoxes) {
+                    nb = 0;  // does not fit the plan: not staged
+                    break;
                 }
+                s_plan.map_idx[nb] = (pitch / kMapWStep - 1) * kMapHCount + (31 - __clz(h));
+                s_plan.row[nb] = row;
+                row += h;
+                rem -= h;
+                ++nb;
             }
-            continue;
+            s_plan.n_boxes = nb;
+            s_plan.x = a0 >> 2;
+            s_plan.y0 = by0;
+            s_plan.bytes = (uint32_t)row * (uint32_t)pitch;
         }
+        __syncthreads();  // s_plan visible; s_box / s_any may be re-initialised by the next item
+        staged = staged && s_plan.n_boxes > 0;
+        const uint32_t stage_bytes = staged ? s_plan.bytes : 0u;
+        const int stage_stride = (int)((stage_bytes + 127u) & ~127u);
+        staged = staged && stage_bytes <= (uint32_t)ring_bytes / 2;
+        const int slog = (staged && 4 * stage_stride <= ring_bytes) ? 2 : 1;
 
-        // ---- consumers ----------------------------------------------------------------------------
-        // dst byte offsets (inside a frame) of the four 32-pixel segments this thread helps to
-        // store: lanes 4q..4q+2 write words 3q..3q+2 of a 96-byte segment
+        // ---- store geometry ---------------------------------------------------------------------
+        // Lanes 4q..4q+2 write words 3q..3q+2 of a 96-byte segment (32 pixels); the four segments
+        // of this warp's tile row are 96 bytes apart.
         const int q = lane >> 2, r4 = lane & 3;
         const uint32_t sel_pack = r4 == 0 ? 0x4210u : (r4 == 1 ? 0x5421u : 0x6542u);
-        bool seg_store[4];
+        const bool lane_st = r4 < 3;
+        bool seg_ok[4];
+        bool full_tile = (y < p.dst_h);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int xs = tile_x * kTileW + 32 * (k & 1);
-            const int y = tile_y * kTileH + 2 * warp + (k >> 1);
-            const int valid_px = min(32, p.dst_w - xs);  // multiple of 4 (dst_w % 4 == 0)
-            seg_store[k] = (y < p.dst_h) && (r4 < 3) && (4 * q < valid_px);
+            const int valid_px = min(32, p.dst_w - (x0 + 32 * k));  // multiple of 4 (dst_w % 4 == 0)
+            seg_ok[k] = (y < p.dst_h) && lane_st && (4 * q < valid_px);
+            full_tile = full_tile && valid_px == 32;
         }
-        // word this lane writes in the left segment of tile row 2*warp; the right segment is
-        // 96 bytes further, the next tile row one dst row further
         long long d_step = (long long)g_stride * p.dst_frame_elems;
-        keep(d_step);
-        const long long row_step = (long long)p.dst_w * 3;
+        asm volatile("" : "+l"(d_step));
         uint8_t *d = dst + (long long)(g_first + f0 * g_stride) * p.dst_frame_elems +
-                     ((long long)(tile_y * kTileH + 2 * warp) * p.dst_w + tile_x * kTileW) * 3 +
-                     (3 * q + r4) * 4;
-        auto store4 = [&](const uint32_t(&word)[4]) {
-            if (seg_store[0]) st_stream(reinterpret_cast<uint32_t *>(d), word[0]);
-            if (seg_store[1]) st_stream(reinterpret_cast<uint32_t *>(d + 96), word[1]);
-            if (seg_store[2]) st_stream(reinterpret_cast<uint32_t *>(d + row_step), word[2]);
-            if (seg_store[3]) st_stream(reinterpret_cast<uint32_t *>(d + row_step + 96), word[3]);
-        };
+                     ((long long)y * p.dst_w + x0) * 3 + (3 * q + r4) * 4;
 
         if (!any) {
             // whole tile maps outside the source: constant border (0) for every frame
 #pragma unroll 1
-            for (int f = f0; f < f1; ++f, d += d_step) {
-                const uint32_t zero[4] = {0u, 0u, 0u, 0u};
-                store4(zero);
-            }
+            for (int i = 0; i < n_frames; ++i, d += d_step)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (seg_ok[k]) st_stream(reinterpret_cast<uint32_t *>(d + 96 * k), 0u);
         } else if (staged) {
-            // frame-invariant per-pixel registers
-            PixLin pl[4];
-            PixNN pn[4];
+            Pix px[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const bool act = (wc0[k] | wc1[k]) != 0;
                 const int A = act ? (rs[k] - by0) * pitch + 3 * cs[k] - a0 : 0;
-                const uint32_t o = A & 3;
+                px[k].addr = A & ~3;
+                px[k].sh = 8 * (A & 3);
                 if (LINEAR) {
-                    pl[k].addr = A & ~3;
-                    pl[k].selA = o | ((o + 3) << 4) | ((o + 1) << 8) | ((o + 4) << 12);
-                    pl[k].wA0 = wc0[k] | (wc1[k] << 8);
-                    pl[k].wA1 = pl[k].wA0 << 16;
-                    // channel 2 lives at window bytes o+2 (tap 0) and o+5 (tap 1)
-                    const uint32_t p2 = o + 2, p5 = o + 5;
-                    const uint32_t e2 = (uint32_t)wc0[k] << (8 * (p2 & 3));
-                    const uint32_t e5 = (uint32_t)wc1[k] << (8 * (p5 & 3));
-                    pl[k].v0 = (p2 < 4 ? e2 : 0u);
-                    pl[k].v1 = (p2 >= 4 ? e2 : 0u) | (p5 < 8 ? e5 : 0u);
-                    pl[k].v2 = (p5 >= 8 ? e5 : 0u);
-                    pl[k].b0 = wr0[k] * 64;
-                    pl[k].b1 = wr1[k] * 64;
-                    pl[k].addr1 = pl[k].addr + pitch;
-                    keep(pl[k].addr);
-                    keep(pl[k].addr1);
-                    keep(pl[k].wA1);
-                    keep(pl[k].b0);
-                    keep(pl[k].b1);
+                    px[k].w03 = wc0[k] | (wc1[k] << 24);
+                    px[k].w16 = wc0[k] | (wc1[k] << 16);
+                    px[k].b0 = wr0[k] * 64;
+                    px[k].b1 = wr1[k] * 64;
                 } else {
-                    pn[k].addr = A & ~3;
-                    pn[k].sel = o | ((o + 1) << 4) | ((o + 2) << 8) | (4u << 12);  // byte 3 is masked off
-                    pn[k].mask = act ? 0x00ffffffu : 0u;
+                    px[k].w03 = act ? 0x00ffffffu : 0u;
+                    px[k].w16 = px[k].b0 = px[k].b1 = 0;
                 }
+                keep(px[k].addr);
+                keep(px[k].sh);
+                keep(px[k].w03);
             }
-
-            int slot = 0;
-#pragma unroll 1
-            for (int f = f0; f < f1; ++f, d += d_step) {
-                mbar_wait(full0 + 8 * slot, (uses >> slot) & 1);
-                uses ^= 1u << slot;
-                const uint32_t sb = ring + slot * stage_stride;
-
-                uint32_t P[4];
-                if (LINEAR) {
-                    uint32_t w[4][6];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        w[k][0] = lds32(sb + pl[k].addr);
-                        w[k][1] = lds32(sb + pl[k].addr + 4);
-                        w[k][2] = lds32(sb + pl[k].addr + 8);
-                        w[k][3] = lds32(sb + pl[k].addr1);
-                        w[k][4] = lds32(sb + pl[k].addr1 + 4);
-                        w[k][5] = lds32(sb + pl[k].addr1 + 8);
-                    }
-                    // all shared-memory reads of this stage are done: hand the slot back early
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(empty0 + 8 * slot);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t ya0 = prmt(w[k][0], w[k][1], pl[k].selA);
-                        const uint32_t ya1 = prmt(w[k][3], w[k][4], pl[k].selA);
-                        // horizontal pass: h[row][channel] = sum over the two taps of a_i * p
-                        const uint32_t h00 = __dp4a(ya0, pl[k].wA0, 0u);
-                        const uint32_t h01 = __dp4a(ya0, pl[k].wA1, 0u);
-                        const uint32_t h10 = __dp4a(ya1, pl[k].wA0, 0u);
-                        const uint32_t h11 = __dp4a(ya1, pl[k].wA1, 0u);
-                        uint32_t h02 = __dp4a(w[k][0], pl[k].v0, 0u);
-                        h02 = __dp4a(w[k][1], pl[k].v1, h02);
-                        h02 = __dp4a(w[k][2], pl[k].v2, h02);
-                        uint32_t h12 = __dp4a(w[k][3], pl[k].v0, 0u);
-                        h12 = __dp4a(w[k][4], pl[k].v1, h12);
-                        h12 = __dp4a(w[k][5], pl[k].v2, h12);
-                        // vertical pass, scaled by 64: byte 2 of t is (sum w*p + 2^14) >> 15
-                        const uint32_t t0 = pl[k].b1 * h10 + (pl[k].b0 * h00 + 32768u);
-                        const uint32_t t1 = pl[k].b1 * h11 + (pl[k].b0 * h01 + 32768u);
-                        const uint32_t t2 = pl[k].b1 * h12 + (pl[k].b0 * h02 + 32768u);
-                        P[k] = prmt(prmt(t0, t1, 0x4462u), t2, 0x7610u);  // [c0, c1, c2, 0]
-                    }
-                } else {
-                    uint32_t w[4][2];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t a = sb + pn[k].addr;
-                        w[k][0] = lds32(a);
-                        w[k][1] = lds32(a + 4);
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(empty0 + 8 * slot);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) P[k] = prmt(w[k][0], w[k][1], pn[k].sel) & pn[k].mask;
-                }
-                // pack 4 lanes x 3 bytes into 3 words and store 96-byte segments
-                uint32_t word[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    word[k] = prmt(P[k], __shfl_down_sync(0xffffffffu, P[k], 1), sel_pack);
-                store4(word);
-                slot = (slot + 1 == n_stages) ? 0 : slot + 1;
-            }
+            LoopCtx c;
+            c.ring = ring;
+            c.full0 = bar0 + (slog == 1 ? 0 : 32);
+            c.empty0 = c.full0 + (slog == 1 ? 16 : 32);
+            c.slog = slog;
+            c.stride = stage_stride;
+            c.pitch = pitch;
+            c.n_frames = n_frames;
+            c.frame0 = g_first + f0 * g_stride;
+            c.frame_step = g_stride;
+            c.src_h = p.src_h;
+            c.maps = &maps;
+            c.plan = &s_plan;
+            keep(c.ring);
+            keep(c.full0);
+            keep(c.empty0);
+            uint32_t use = (slog == 1) ? use_a : use_b;
+            if (full_tile)
+                use = frame_loop<LINEAR, true>(c, px, use, d, d_step, lane_st, seg_ok, sel_pack);
+            else
+                use = frame_loop<LINEAR, false>(c, px, use, d, d_step, lane_st, seg_ok, sel_pack);
+            if (slog == 1)
+                use_a = use;
+            else
+                use_b = use;
         } else {
-            // bounding box larger than half the ring (extreme minification): same arithmetic
-            // straight from global memory
+            // bounding box too large for the ring (extreme minification) or too wide / tall for
+            // the tensor-map menu: same arithmetic straight from global memory
             const uint8_t *s = src + (long long)(g_first + f0 * g_stride) * p.src_frame_elems;
             const long long s_step = (long long)g_stride * p.src_frame_elems;
 #pragma unroll 1
-            for (int f = f0; f < f1; ++f, d += d_step, s += s_step) {
+            for (int i = 0; i < n_frames; ++i, d += d_step, s += s_step) {
                 uint32_t P[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const uint8_t *t = s + (long long)rs[k] * src_row_bytes + 3 * cs[k];
-                    uint32_t px = 0;
+                    uint32_t pxv = 0;
                     if (LINEAR) {
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            const int h0 = wc0[k] * __ldg(t + c) + wc1[k] * __ldg(t + 3 + c);
-                            const int h1 = wc0[k] * __ldg(t + src_row_bytes + c) +
-                                           wc1[k] * __ldg(t + src_row_bytes + 3 + c);
+                        for (int ch = 0; ch < 3; ++ch) {
+                            const int h0 = wc0[k] * __ldg(t + ch) + wc1[k] * __ldg(t + 3 + ch);
+                            const int h1 = wc0[k] * __ldg(t + src_row_bytes + ch) +
+                                           wc1[k] * __ldg(t + src_row_bytes + 3 + ch);
                             const uint32_t v = (uint32_t)(wr0[k] * h0 + wr1[k] * h1 + 512) >> 10;
-                            px |= v << (8 * c);
+                            pxv |= v << (8 * ch);
                         }
                     } else if (wc0[k]) {
-                        px = __ldg(t) | (__ldg(t + 1) << 8) | (__ldg(t + 2) << 16);
+                        pxv = __ldg(t) | (__ldg(t + 1) << 8) | (__ldg(t + 2) << 16);
                     }
-                    P[k] = px;
+                    P[k] = pxv;
                 }
-                uint32_t word[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    word[k] = prmt(P[k], __shfl_down_sync(0xffffffffu, P[k], 1), sel_pack);
-                store4(word);
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t word = prmt(P[k], __shfl_down_sync(0xffffffffu, P[k], 1), sel_pack);
+                    if (seg_ok[k]) st_stream(reinterpret_cast<uint32_t *>(d + 96 * k), word);
+                }
             }
         }
     }
+}
+
+// ---- host side: tensor-map menu ---------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct MapCacheEntry {
+    const void *base = nullptr;
+    int row_bytes = 0;
+    long long rows = 0;
+    unsigned long long stamp = 0;
+    WarpFastMaps maps;
+};
+constexpr int kMapCacheSize = 8;
+MapCacheEntry g_map_cache[kMapCacheSize];
+unsigned long long g_map_stamp = 0;
+std::mutex g_map_mutex;
+EncodeTiledFn g_encode = nullptr;
+
+// The batch viewed as a [rows][row_bytes / 4] uint32 matrix: one tensor map per box shape.
+int get_maps(const void *base, int row_bytes, long long rows, WarpFastMaps &out)
+{
+    std::lock_guard<std::mutex> lock(g_map_mutex);
+    if (!g_encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        BEVK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !fn)
+            BEVK_FAIL(BEVK_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        g_encode = (EncodeTiledFn)fn;
+    }
+    MapCacheEntry *victim = &g_map_cache[0];
+    for (int i = 0; i < kMapCacheSize; ++i) {
+        MapCacheEntry &e = g_map_cache[i];
+        if (e.base == base && e.row_bytes == row_bytes && e.rows == rows) {
+            e.stamp = ++g_map_stamp;
+            out = e.maps;
+            return BEVK_OK;
+        }
+        if (e.stamp < victim->stamp) victim = &e;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)(row_bytes / 4), (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)row_bytes};
+    const cuuint32_t estride[2] = {1, 1};
+    for (int wi = 0; wi < kMapWCount; ++wi)
+        for (int hi = 0; hi < kMapHCount; ++hi) {
+            const cuuint32_t box[2] = {(cuuint32_t)((wi + 1) * kMapWStep / 4), (cuuint32_t)(1u << hi)};
+            CUresult r = g_encode(&victim->maps.m[wi * kMapHCount + hi], CU_TENSOR_MAP_DATA_TYPE_UINT32,
+                                  2, const_cast<void *>(base), gdim, gstride, box, estride,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) {
+                victim->base = nullptr;
+                BEVK_FAIL(BEVK_E_CUDA, "cuTensorMapEncodeTiled failed (code %d) for a %ux%u box",
+                          (int)r, box[0] * 4, box[1]);
+            }
+        }
+    victim->base = base;
+    victim->row_bytes = row_bytes;
+    victim->rows = rows;
+    victim->stamp = ++g_map_stamp;
+    out = victim->maps;
+    return BEVK_OK;
+}
+
+struct KernelConfig {
+    bool ready = false;
+    int ctas_per_sm = 0;
+    int ring_bytes = 0;
+};
+KernelConfig g_cfg[2];
+
+template <bool LINEAR> int configure(KernelConfig &cfg)
+{
+    auto kern = warp_fast_u8c3_kernel<LINEAR>;
+    // how many CTAs the register file allows, then split the shared memory evenly between them
+    BEVK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1024));
+    int by_regs = 0;
+    BEVK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&by_regs, kern, kThreads, 16 * 1024));
+    if (by_regs < 1) BEVK_FAIL(BEVK_E_CUDA, "staged warp kernel does not fit an SM");
+    by_regs = by_regs > 4 ? 4 : by_regs;
+    int dev = 0, smem_sm = 0;
+    BEVK_CUDA(cudaGetDevice(&dev));
+    BEVK_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+    // per CTA: 1 KB reserved by the driver + static shared memory
+    int ring = smem_sm / by_regs - 1024 - 512 - kBarBytes - kTailSlack;
+    ring &= ~127;
+    if (ring > 200 * 1024) ring = 200 * 1024;
+    BEVK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   ring + kBarBytes + kTailSlack));
+    cfg.ctas_per_sm = by_regs;
+    cfg.ring_bytes = ring;
+    cfg.ready = true;
+    return BEVK_OK;
 }
 
 }  // namespace
@@ -453,35 +615,52 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p, const int tiles_
 int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, int linear,
                           cudaStream_t stream)
 {
-    // qualification: uint8 x 3, zero border, rows that the bulk copy / word stores can address
+    // qualification: uint8 x 3, zero border, rows the tensor maps / word stores can address
     if (dtype != BEVK_U8 || channels != 3) return 0;
     if (p_in.border[0] != 0.f || p_in.border[1] != 0.f || p_in.border[2] != 0.f) return 0;
     if (p_in.src_w < 2 || p_in.src_h < 2) return 0;
     if ((p_in.src_w * 3) % 16 != 0 || (p_in.dst_w % 4) != 0) return 0;
     if (((uintptr_t)p_in.src % 16) != 0 || ((uintptr_t)p_in.dst % 4) != 0) return 0;
 
-    static bool attr_set[2] = {false, false};
-    auto kern = linear ? warp_fast_u8c3_kernel<true> : warp_fast_u8c3_kernel<false>;
-    if (!attr_set[linear ? 1 : 0]) {
-        BEVK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        attr_set[linear ? 1 : 0] = true;
+    KernelConfig &cfg = g_cfg[linear ? 1 : 0];
+    if (!cfg.ready) {
+        int rc = linear ? configure<true>(cfg) : configure<false>(cfg);
+        if (rc) return rc;
     }
 
     BevkWarpParams p = p_in;
+    int n_src_frames = 0, max_count = 0;
+    for (int i = 0; i < p.n_groups; ++i) {
+        const int last = p.g[i].first + (p.g[i].count - 1) * p.g[i].stride;
+        n_src_frames = n_src_frames > last + 1 ? n_src_frames : last + 1;
+        max_count = max_count > p.g[i].count ? max_count : p.g[i].count;
+    }
+    const long long rows = (long long)n_src_frames * p.src_h;
+    if (rows > 0x7fffffffLL) return 0;  // TMA coordinates are int32
+    WarpFastMaps maps;
+    int rc = get_maps(p.src, p.src_w * 3, rows, maps);
+    if (rc) return rc;
+
     const int tiles_x = (p.dst_w + kTileW - 1) / kTileW, tiles_y = (p.dst_h + kTileH - 1) / kTileH;
     const long long n_tiles = (long long)tiles_x * tiles_y;
-    const int ctas = bevk_sm_count() * 2;
-    int max_count = 0;
-    for (int i = 0; i < p.n_groups; ++i) max_count = max_count > p.g[i].count ? max_count : p.g[i].count;
-    // frames per chunk: as many as possible (amortises the FP64 set-up) while keeping at least
-    // ~4 items per resident CTA for balance
-    int fpc = max_count < 64 ? max_count : 64;
-    while (fpc > 8) {
+    const int ctas = bevk_sm_count() * cfg.ctas_per_sm;
+    // frames per chunk: long chunks amortise the FP64 set-up, but the item count should fill
+    // whole rounds of resident CTAs.  cost(chunks) ~ rounds * (set-up + frames per chunk).
+    const double setup_frames = 4.0;
+    int best_chunks = 1;
+    double best_cost = 1e300;
+    for (int chunks = 1; chunks <= 16 && chunks <= max_count; ++chunks) {
+        const int fpc = (max_count + chunks - 1) / chunks;
         long long items = 0;
         for (int i = 0; i < p.n_groups; ++i) items += n_tiles * ((p.g[i].count + fpc - 1) / fpc);
-        if (items >= 4LL * ctas) break;
-        fpc = (fpc + 1) / 2;
+        const double rounds = (double)((items + ctas - 1) / ctas);
+        const double cost = rounds * (setup_frames + fpc);
+        if (cost < best_cost * 0.999) {
+            best_cost = cost;
+            best_chunks = chunks;
+        }
     }
+    const int fpc = (max_count + best_chunks - 1) / best_chunks;
     p.frames_per_chunk = fpc;
     long long items = 0;
     for (int i = 0; i < p.n_groups; ++i) {
@@ -491,7 +670,13 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
     if (items > 0x7fffffffLL) return 0;
     p.total_chunks = (int)items;
     const int grid = (int)(items < ctas ? items : ctas);
-    kern<<<grid, kThreads + 32, kSmemBytes, stream>>>(p, tiles_x, tiles_y, (int)items);
+    const int smem = cfg.ring_bytes + kBarBytes + kTailSlack;
+    if (linear)
+        warp_fast_u8c3_kernel<true><<<grid, kThreads, smem, stream>>>(p, maps, tiles_x, tiles_y,
+                                                                    (int)items, cfg.ring_bytes);
+    else
+        warp_fast_u8c3_kernel<false><<<grid, kThreads, smem, stream>>>(p, maps, tiles_x, tiles_y,
+                                                                     (int)items, cfg.ring_bytes);
     BEVK_CUDA(cudaGetLastError());
     return 1;
 }
