@@ -45,7 +45,8 @@ constexpr int kTileW = 128, kTileH = 8, kThreads = 256, kWarps = kThreads / 32;
 constexpr int kMapWStep = 64, kMapWCount = 16;  // box widths 64, 128, ..., 1024 bytes
 constexpr int kMapHCount = 7;                   // box heights 1, 2, 4, ..., 64 rows
 constexpr int kMaxBoxes = 3;
-constexpr int kBarBytes = 128;                  // 12 mbarriers
+constexpr int kBarBytes = 256;                  // 28 mbarriers: ring depths 2, 4 and 8
+constexpr int kPrefetchAhead = 3;               // L2 prefetch runs this many frames ahead of the ring
 constexpr int kTailSlack = 64;                  // window words may run a few bytes past a stage
 
 struct WarpFastMaps {
@@ -93,6 +94,14 @@ __device__ __forceinline__ void tma_box_g2s(uint32_t dst, const CUtensorMap *map
         " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
         "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(x), "r"(y)
         : "memory");
+}
+// the same box, global -> L2 only (no shared memory, no completion)
+__device__ __forceinline__ void tma_box_prefetch(const CUtensorMap *map, int x, int y)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(x), "r"(y)
+                 : "memory");
 }
 __device__ __forceinline__ uint32_t lds32(uint32_t addr)
 {
@@ -174,7 +183,6 @@ __device__ __forceinline__ uint32_t lerp_pixel(const Pix &q, uint32_t r0, uint32
 
 struct LoopCtx {
     uint32_t ring, full0, empty0;  // shared-memory addresses of the ring / first barrier of the set
-    uint32_t slog;                 // log2(ring depth)
     uint32_t stride;               // bytes per stage
     uint32_t pitch;                // bytes per staged row
     int n_frames;
@@ -184,41 +192,71 @@ struct LoopCtx {
     const BoxPlan *plan;           // in shared memory
 };
 
-// Elected thread: start the copy of frame `i` of the item into its ring slot.  `use` is the
-// running count of stages this CTA has pushed through the barrier set.
+// Elected thread: pull frame `i` of the item towards the SM.  TO_SMEM starts the copy into its
+// ring slot (`use` is the running count of stages this CTA has pushed through the barrier set);
+// otherwise the boxes are only prefetched into L2, kPrefetchAhead frames ahead of the ring, so
+// that the later copy does not wait on HBM.
+template <int SLOG, bool TO_SMEM>
 __device__ __forceinline__ void produce(const LoopCtx &c, int i, uint32_t use)
 {
-    const uint32_t slot = use & ((1u << c.slog) - 1u);
-    // k-th fill of a slot waits for the (k-1)-th release; the first passes at once
-    mbar_wait(c.empty0 + 8 * slot, ((use >> c.slog) & 1u) ^ 1u);
-    const uint32_t fb = c.full0 + 8 * slot;
-    mbar_expect_tx(fb, c.plan->bytes);
     const int y = (c.frame0 + i * c.frame_step) * c.src_h + c.plan->y0;
-    const uint32_t sdst = c.ring + slot * c.stride;
     const int nb = c.plan->n_boxes;
+    if (TO_SMEM) {
+        const uint32_t slot = use & ((1u << SLOG) - 1u);
+        // k-th fill of a slot waits for the (k-1)-th release; the first passes at once
+        mbar_wait(c.empty0 + 8 * slot, ((use >> SLOG) & 1u) ^ 1u);
+        const uint32_t fb = c.full0 + 8 * slot;
+        mbar_expect_tx(fb, c.plan->bytes);
+        const uint32_t sdst = c.ring + slot * c.stride;
 #pragma unroll 1
-    for (int b = 0; b < nb; ++b)
-        tma_box_g2s(sdst + c.plan->row[b] * c.pitch, &c.maps->m[c.plan->map_idx[b]], c.plan->x,
-                    y + c.plan->row[b], fb);
+        for (int b = 0; b < nb; ++b)
+            tma_box_g2s(sdst + c.plan->row[b] * c.pitch, &c.maps->m[c.plan->map_idx[b]], c.plan->x,
+                        y + c.plan->row[b], fb);
+    } else {
+#pragma unroll 1
+        for (int b = 0; b < nb; ++b)
+            tma_box_prefetch(&c.maps->m[c.plan->map_idx[b]], c.plan->x, y + c.plan->row[b]);
+    }
+}
+
+// Iteration i of the frame loop: keep the ring and the L2 prefetch window full.  The producer role
+// rotates over the warps (one elected lane each) so that no warp is slower than the others --
+// a fixed producer warp paces the whole CTA, because every warp waits on the stages it issues.
+template <int SLOG>
+__device__ __forceinline__ void feed(const LoopCtx &c, int i, uint32_t use, int lane, int warp)
+{
+    constexpr int ahead = 1 << (SLOG - 1);
+    if (lane != 0) return;
+    const int turn = (i - warp) & (kWarps - 1);
+    if (turn == 0 && i + ahead < c.n_frames) produce<SLOG, true>(c, i + ahead, use + ahead);
+    if (turn == kWarps / 2 && i + ahead + kPrefetchAhead < c.n_frames)
+        produce<SLOG, false>(c, i + ahead + kPrefetchAhead, 0);
 }
 
 // The frame loop of a staged item.  FULL: every pixel of the tile is inside the dst image.
-template <bool LINEAR, bool FULL>
+// Ring depth 2^SLOG.  Returns the advanced stage counter.
+template <bool LINEAR, bool FULL, int SLOG>
 __device__ __forceinline__ uint32_t frame_loop(const LoopCtx &c, const Pix (&px)[4], uint32_t use,
-                                               uint8_t *d, const long long d_step,
+                                               uint8_t *d, const uint32_t d_step,
                                                const bool lane_st, const bool (&seg_ok)[4],
-                                               const uint32_t sel_pack)
+                                               const uint32_t sel_pack, const int tid)
 {
-    const int tid = threadIdx.x, lane = tid & 31;
-    const uint32_t smask = (1u << c.slog) - 1u;
-    const int ahead = (int)smask;  // frames in flight besides the one being consumed
-    if (tid == 0)
-        for (int i = 0; i < ahead && i < c.n_frames; ++i) produce(c, i, use + i);
+    constexpr uint32_t smask = (1u << SLOG) - 1u;
+    // Frames in flight besides the one being consumed: half the ring.  The other half is slack
+    // between the warps -- a slot is refilled S/2 frames after its last use, so the refilling lane
+    // practically never waits for a slower warp to release it.
+    constexpr int ahead = 1 << (SLOG - 1);
+    const int lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int i = 0; i < ahead && i < c.n_frames; ++i) produce<SLOG, true>(c, i, use + i);
+        for (int i = ahead; i < ahead + kPrefetchAhead && i < c.n_frames; ++i)
+            produce<SLOG, false>(c, i, 0);
+    }
 
 #pragma unroll 1
     for (int i = 0; i < c.n_frames; ++i, d += d_step) {
         const uint32_t slot = use & smask;
-        mbar_wait(c.full0 + 8 * slot, (use >> c.slog) & 1u);
+        mbar_wait(c.full0 + 8 * slot, (use >> SLOG) & 1u);
         const uint32_t sa = c.ring + slot * c.stride;  // row 0 of the windows
         const uint32_t sb = sa + c.pitch;              // row 1
         uint32_t P[4];
@@ -232,7 +270,7 @@ __device__ __forceinline__ uint32_t frame_loop(const LoopCtx &c, const Pix (&px)
                     // all shared-memory reads of this stage are issued: hand the slot back early
                     __syncwarp();
                     if (lane == 0) mbar_arrive(c.empty0 + 8 * slot);
-                    if (tid == 0 && i + ahead < c.n_frames) produce(c, i + ahead, use + ahead);
+                    feed<SLOG>(c, i, use, lane, warp);
                 }
                 P[k] = lerp_pixel(px[k], r0, r1, r2, s0, s1, s2);
             }
@@ -245,7 +283,7 @@ __device__ __forceinline__ uint32_t frame_loop(const LoopCtx &c, const Pix (&px)
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(c.empty0 + 8 * slot);
-            if (tid == 0 && i + ahead < c.n_frames) produce(c, i + ahead, use + ahead);
+            feed<SLOG>(c, i, use, lane, warp);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 P[k] = __funnelshift_r(w[k][0], w[k][1], px[k].sh) & px[k].w03;
@@ -261,6 +299,18 @@ __device__ __forceinline__ uint32_t frame_loop(const LoopCtx &c, const Pix (&px)
     return use;
 }
 
+template <bool LINEAR, int SLOG>
+__device__ __forceinline__ uint32_t frame_loop_any(const bool full_tile, const LoopCtx &c,
+                                                   const Pix (&px)[4], uint32_t use, uint8_t *d,
+                                                   const uint32_t d_step, const bool lane_st,
+                                                   const bool (&seg_ok)[4], const uint32_t sel_pack,
+                                                   const int tid)
+{
+    if (full_tile)
+        return frame_loop<LINEAR, true, SLOG>(c, px, use, d, d_step, lane_st, seg_ok, sel_pack, tid);
+    return frame_loop<LINEAR, false, SLOG>(c, px, use, d, d_step, lane_st, seg_ok, sel_pack, tid);
+}
+
 template <bool LINEAR>
 __global__ void __launch_bounds__(kThreads, 4)
 warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
@@ -268,24 +318,30 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
                       const int tiles_y, const int total_items, const int ring_bytes)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    // barrier set A (ring depth 2): full[2], empty[2]; set B (depth 4): full[4], empty[4]
+    // three barrier sets, one per ring depth S = 2, 4, 8: full[S] then empty[S], at byte
+    // offsets 0, 32 and 96.  Each set keeps its own running stage counter (s_use) across items,
+    // so barrier phases never need a reset when consecutive items use different depths.
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + ring_bytes);
     __shared__ int s_box[4];
     __shared__ int s_any;
+    __shared__ uint32_t s_use[3];
     __shared__ BoxPlan s_plan;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t ring = smem_u32(smem);
     const uint32_t bar0 = smem_u32(bars);
     if (tid == 0) {
-        for (int i = 0; i < 12; ++i) {
-            const bool is_full = (i < 2) || (i >= 4 && i < 8);
-            mbar_init(bar0 + 8 * i, is_full ? 1 : kWarps);
+        for (int sl = 1; sl <= 3; ++sl) {
+            const int S = 1 << sl, base = 16 * S - 32;
+            for (int i = 0; i < S; ++i) {
+                mbar_init(bar0 + base + 8 * i, 1);                // full: the producer's expect_tx
+                mbar_init(bar0 + base + 8 * (S + i), kWarps);     // empty: one arrival per warp
+            }
+            s_use[sl - 1] = 0;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    uint32_t use_a = 0, use_b = 0;  // stages pushed through barrier set A / B so far
 
     const int n_tiles = tiles_x * tiles_y;
     const uint8_t *src = (const uint8_t *)p.src;
@@ -403,7 +459,7 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
         const uint32_t stage_bytes = staged ? s_plan.bytes : 0u;
         const int stage_stride = (int)((stage_bytes + 127u) & ~127u);
         staged = staged && stage_bytes <= (uint32_t)ring_bytes / 2;
-        const int slog = (staged && 4 * stage_stride <= ring_bytes) ? 2 : 1;
+        const int slog = (8 * stage_stride <= ring_bytes) ? 3 : (4 * stage_stride <= ring_bytes ? 2 : 1);
 
         // ---- store geometry ---------------------------------------------------------------------
         // Lanes 4q..4q+2 write words 3q..3q+2 of a 96-byte segment (32 pixels); the four segments
@@ -419,8 +475,8 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
             seg_ok[k] = (y < p.dst_h) && lane_st && (4 * q < valid_px);
             full_tile = full_tile && valid_px == 32;
         }
-        long long d_step = (long long)g_stride * p.dst_frame_elems;
-        asm volatile("" : "+l"(d_step));
+        uint32_t d_step = (uint32_t)g_stride * (uint32_t)p.dst_frame_elems;  // < 2^32 (host check)
+        keep(d_step);
         uint8_t *d = dst + (long long)(g_first + f0 * g_stride) * p.dst_frame_elems +
                      ((long long)y * p.dst_w + x0) * 3 + (3 * q + r4) * 4;
 
@@ -454,9 +510,8 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
             }
             LoopCtx c;
             c.ring = ring;
-            c.full0 = bar0 + (slog == 1 ? 0 : 32);
-            c.empty0 = c.full0 + (slog == 1 ? 16 : 32);
-            c.slog = slog;
+            c.full0 = bar0 + 16 * (1 << slog) - 32;
+            c.empty0 = c.full0 + 8 * (1 << slog);
             c.stride = stage_stride;
             c.pitch = pitch;
             c.n_frames = n_frames;
@@ -468,15 +523,16 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
             keep(c.ring);
             keep(c.full0);
             keep(c.empty0);
-            uint32_t use = (slog == 1) ? use_a : use_b;
-            if (full_tile)
-                use = frame_loop<LINEAR, true>(c, px, use, d, d_step, lane_st, seg_ok, sel_pack);
+            // every thread tracks the counter in a register; thread 0 publishes it for the next item
+            uint32_t use = s_use[slog - 1];
+            if (slog == 3)
+                use = frame_loop_any<LINEAR, 3>(full_tile, c, px, use, d, d_step, lane_st, seg_ok, sel_pack, tid);
+            else if (slog == 2)
+                use = frame_loop_any<LINEAR, 2>(full_tile, c, px, use, d, d_step, lane_st, seg_ok, sel_pack, tid);
             else
-                use = frame_loop<LINEAR, false>(c, px, use, d, d_step, lane_st, seg_ok, sel_pack);
-            if (slog == 1)
-                use_a = use;
-            else
-                use_b = use;
+                use = frame_loop_any<LINEAR, 1>(full_tile, c, px, use, d, d_step, lane_st, seg_ok, sel_pack, tid);
+            __syncthreads();  // every warp has read s_use and left the ring
+            if (tid == 0) s_use[slog - 1] = use;
         } else {
             // bounding box too large for the ring (extreme minification) or too wide / tall for
             // the tensor-map menu: same arithmetic straight from global memory
@@ -615,7 +671,8 @@ template <bool LINEAR> int configure(KernelConfig &cfg)
 int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, int linear,
                           cudaStream_t stream)
 {
-    // qualification: uint8 x 3, zero border, rows the tensor maps / word stores can address
+    // qualification: uint8 x 3, zero border, rows the tensor maps / word stores can address,
+    // per-frame dst pointer steps that fit 32 bits
     if (dtype != BEVK_U8 || channels != 3) return 0;
     if (p_in.border[0] != 0.f || p_in.border[1] != 0.f || p_in.border[2] != 0.f) return 0;
     if (p_in.src_w < 2 || p_in.src_h < 2) return 0;
@@ -630,6 +687,8 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
 
     BevkWarpParams p = p_in;
     int n_src_frames = 0, max_count = 0;
+    for (int i = 0; i < p.n_groups; ++i)
+        if ((long long)p.g[i].stride * p.dst_frame_elems > 0xffffffffLL || p.g[i].stride < 1) return 0;
     for (int i = 0; i < p.n_groups; ++i) {
         const int last = p.g[i].first + (p.g[i].count - 1) * p.g[i].stride;
         n_src_frames = n_src_frames > last + 1 ? n_src_frames : last + 1;
