@@ -53,6 +53,15 @@ struct WarpFastMaps {
     CUtensorMap m[kMapWCount * kMapHCount];
 };
 
+// Frame chunks of one launch.  Chunk k of a group with `count` frames covers frames
+// [count * cum[k] >> 16, count * cum[k + 1] >> 16): the chunks shrink towards the end of the item
+// list, so that the CTAs, which pull items from a shared counter, finish almost together.
+constexpr int kMaxChunks = 12;
+struct ChunkPlan {
+    int n_chunks;
+    uint32_t cum[kMaxChunks + 1];  // cum[0] = 0, cum[n_chunks] = 65536
+};
+
 // ---- PTX wrappers -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
@@ -119,15 +128,6 @@ __device__ __forceinline__ void st_stream(uint32_t *p, uint32_t v)
 }
 // Stops the compiler from re-deriving a loop-invariant value inside the frame loop.
 __device__ __forceinline__ void keep(uint32_t &v) { asm volatile("" : "+r"(v)); }
-
-__device__ __forceinline__ int find_group_item(const BevkWarpParams &p, int item)
-{
-    int gi = 0;
-#pragma unroll 1
-    for (int i = 1; i < p.n_groups; ++i)
-        if (item >= p.g[i].chunk0) gi = i;
-    return gi;
-}
 
 // 2-tap window along one axis: first index (clamped into the image) and the weight each of the
 // two window positions receives.  Taps outside [0, n) contribute nothing (border value 0).
@@ -314,8 +314,9 @@ __device__ __forceinline__ uint32_t frame_loop_any(const bool full_tile, const L
 template <bool LINEAR>
 __global__ void __launch_bounds__(kThreads, 4)
 warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
-                      const __grid_constant__ WarpFastMaps maps, const int tiles_x,
-                      const int tiles_y, const int total_items, const int ring_bytes)
+                      const __grid_constant__ WarpFastMaps maps,
+                      const __grid_constant__ ChunkPlan plan, const int tiles_x, const int tiles_y,
+                      const int total_items, const int ring_bytes, int *const next_item)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     // three barrier sets, one per ring depth S = 2, 4, 8: full[S] then empty[S], at byte
@@ -325,6 +326,7 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
     __shared__ int s_box[4];
     __shared__ int s_any;
     __shared__ uint32_t s_use[3];
+    __shared__ int s_next;
     __shared__ BoxPlan s_plan;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -348,18 +350,22 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
     uint8_t *dst = (uint8_t *)p.dst;
     const int src_row_bytes = p.src_w * 3;
 
+    // Items are (chunk, group, tile) with the chunk index slowest: long chunks first.  The first
+    // gridDim.x items are taken by block index, the rest are pulled from *next_item.
+    const int per_chunk = p.n_groups * n_tiles;
+    int item = blockIdx.x;
 #pragma unroll 1
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int gi = find_group_item(p, item);
+    while (item < total_items) {
+        const int chunk = item / per_chunk, rem = item - chunk * per_chunk;
+        const int gi = rem / n_tiles, tile = rem - gi * n_tiles;
         const int g_first = p.g[gi].first, g_stride = p.g[gi].stride, g_count = p.g[gi].count;
-        const int local = item - p.g[gi].chunk0;
-        const int chunk = local / n_tiles, tile = local - chunk * n_tiles;
         // column-major walk: concurrently running CTAs cover whole tile columns, i.e. both the
         // magnified far field (store-heavy) and the minified near field (load-heavy)
         const int tile_x = tile / tiles_y, tile_y = tile - tile_x * tiles_y;
-        const int f0 = chunk * p.frames_per_chunk;
-        const int n_frames = min(f0 + p.frames_per_chunk, g_count) - f0;
+        const int f0 = (int)(((unsigned long long)g_count * plan.cum[chunk]) >> 16);
+        const int n_frames = (int)(((unsigned long long)g_count * plan.cum[chunk + 1]) >> 16) - f0;
         const int x0 = tile_x * kTileW, y = tile_y * kTileH + warp;
+        if (tid == 0) s_next = next_item ? (int)gridDim.x + atomicAdd(next_item, 1) : item + (int)gridDim.x;
 
         // ---- 1. set-up ------------------------------------------------------------------------
         if (tid == 0) {
@@ -420,6 +426,7 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
         }
         __syncthreads();
         const bool any = s_any != 0;
+        item = s_next;
         bx0 = s_box[0];
         bx1 = s_box[1];
         by0 = s_box[2];
@@ -588,6 +595,11 @@ unsigned long long g_map_stamp = 0;
 std::mutex g_map_mutex;
 EncodeTiledFn g_encode = nullptr;
 
+constexpr int kCounterSlots = 1024;
+int *g_counters = nullptr;
+int g_counters_dev = -1;
+unsigned g_counter_next = 0;
+
 // The batch viewed as a [rows][row_bytes / 4] uint32 matrix: one tensor map per box shape.
 int get_maps(const void *base, int row_bytes, long long rows, WarpFastMaps &out)
 {
@@ -703,39 +715,55 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
     const int tiles_x = (p.dst_w + kTileW - 1) / kTileW, tiles_y = (p.dst_h + kTileH - 1) / kTileH;
     const long long n_tiles = (long long)tiles_x * tiles_y;
     const int ctas = bevk_sm_count() * cfg.ctas_per_sm;
-    // frames per chunk: long chunks amortise the FP64 set-up, but the item count should fill
-    // whole rounds of resident CTAs.  cost(chunks) ~ rounds * (set-up + frames per chunk).
-    const double setup_frames = 4.0;
-    int best_chunks = 1;
-    double best_cost = 1e300;
-    for (int chunks = 1; chunks <= 16 && chunks <= max_count; ++chunks) {
-        const int fpc = (max_count + chunks - 1) / chunks;
-        long long items = 0;
-        for (int i = 0; i < p.n_groups; ++i) items += n_tiles * ((p.g[i].count + fpc - 1) / fpc);
-        const double rounds = (double)((items + ctas - 1) / ctas);
-        const double cost = rounds * (setup_frames + fpc);
-        if (cost < best_cost * 0.999) {
-            best_cost = cost;
-            best_chunks = chunks;
-        }
+
+    // Frame chunks.  Every (tile, chunk) item pays one FP64 set-up, so chunks should be long; the
+    // CTAs pull items from a shared counter, so the LAST items should be short.  With enough
+    // frames the chunk lengths therefore decay (1/4, 1/4, 3/16, 1/8, 3/32, 1/16, 1/32 of the
+    // frames); short batches get fewer, equal chunks, just enough for ~3 items per CTA.
+    ChunkPlan plan;
+    memset(&plan, 0, sizeof(plan));
+    const long long tile_groups = n_tiles * p.n_groups;
+    if (max_count >= 128 && tile_groups * 7 >= 2LL * ctas) {
+        static const uint32_t cum[8] = {0, 16384, 32768, 45056, 53248, 59392, 63488, 65536};
+        plan.n_chunks = 7;
+        memcpy(plan.cum, cum, sizeof(cum));
+    } else {
+        int k = (int)((3LL * ctas + tile_groups - 1) / tile_groups);
+        k = k < 1 ? 1 : k;
+        k = k > kMaxChunks ? kMaxChunks : k;
+        k = k > (max_count + 7) / 8 ? (max_count + 7) / 8 : k;  // at least ~8 frames per chunk
+        k = k < 1 ? 1 : k;
+        plan.n_chunks = k;
+        for (int i = 0; i <= k; ++i) plan.cum[i] = (uint32_t)(65536LL * i / k);
     }
-    const int fpc = (max_count + best_chunks - 1) / best_chunks;
-    p.frames_per_chunk = fpc;
-    long long items = 0;
-    for (int i = 0; i < p.n_groups; ++i) {
-        p.g[i].chunk0 = (int)items;
-        items += n_tiles * ((p.g[i].count + fpc - 1) / fpc);
-    }
+    const long long items = tile_groups * plan.n_chunks;
     if (items > 0x7fffffffLL) return 0;
-    p.total_chunks = (int)items;
     const int grid = (int)(items < ctas ? items : ctas);
+
+    // shared item counter: one zeroed slot per launch out of a ring (launches on different
+    // streams may overlap).  Not needed when every CTA has exactly one item.
+    int *counter = nullptr;
+    if (items > grid) {
+        std::lock_guard<std::mutex> lock(g_map_mutex);
+        int dev = 0;
+        BEVK_CUDA(cudaGetDevice(&dev));
+        if (!g_counters || g_counters_dev != dev) {
+            if (g_counters) cudaFree(g_counters);
+            g_counters = nullptr;
+            BEVK_CUDA(cudaMalloc(&g_counters, kCounterSlots * sizeof(int)));
+            g_counters_dev = dev;
+        }
+        counter = g_counters + (g_counter_next++ % kCounterSlots);
+    }
+    if (counter) BEVK_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));
+
     const int smem = cfg.ring_bytes + kBarBytes + kTailSlack;
     if (linear)
-        warp_fast_u8c3_kernel<true><<<grid, kThreads, smem, stream>>>(p, maps, tiles_x, tiles_y,
-                                                                    (int)items, cfg.ring_bytes);
+        warp_fast_u8c3_kernel<true><<<grid, kThreads, smem, stream>>>(
+            p, maps, plan, tiles_x, tiles_y, (int)items, cfg.ring_bytes, counter);
     else
-        warp_fast_u8c3_kernel<false><<<grid, kThreads, smem, stream>>>(p, maps, tiles_x, tiles_y,
-                                                                     (int)items, cfg.ring_bytes);
+        warp_fast_u8c3_kernel<false><<<grid, kThreads, smem, stream>>>(
+            p, maps, plan, tiles_x, tiles_y, (int)items, cfg.ring_bytes, counter);
     BEVK_CUDA(cudaGetLastError());
     return 1;
 }
