@@ -37,17 +37,36 @@
 
 #include <cuda.h>  // CUtensorMap + enums only; the encoder is fetched through the runtime
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
 
 namespace {
 
 constexpr int kTileW = 128, kTileH = 8, kThreads = 256, kWarps = kThreads / 32;
-constexpr int kMapWStep = 64, kMapWCount = 16;  // box widths 64, 128, ..., 1024 bytes
-constexpr int kMapHCount = 7;                   // box heights 1, 2, 4, ..., 64 rows
+// Tensor-map menu: one map per box shape.  Widths 64..512 B in steps of 64 and 640..1024 B in steps
+// of 128; heights 1..8, 10..16 in steps of 2, 20..32 in steps of 4.  A tile's bounding box is
+// fetched with one box whenever it has at most 32 rows (taller ones take up to kMaxBoxes).
+constexpr int kMapWCount = 12, kMapHCount = 16, kMaxBoxWidth = 1024, kMaxBoxHeight = 32;
 constexpr int kMaxBoxes = 3;
+constexpr int kMaxStageFrames = 4;              // frames that share one ring stage / mbarrier phase
 constexpr int kBarBytes = 256;                  // 28 mbarriers: ring depths 2, 4 and 8
-constexpr int kPrefetchAhead = 3;               // L2 prefetch runs this many frames ahead of the ring
+constexpr int kPrefetchAhead = 2;               // depth-2 rings: L2 prefetch runs this many stages ahead
 constexpr int kTailSlack = 64;                  // window words may run a few bytes past a stage
+
+__host__ __device__ constexpr int map_width(int wi) { return wi < 8 ? 64 * (wi + 1) : 512 + 128 * (wi - 7); }
+__host__ __device__ constexpr int map_height(int hi)
+{
+    return hi < 8 ? hi + 1 : (hi < 12 ? 10 + 2 * (hi - 8) : 20 + 4 * (hi - 12));
+}
+// smallest menu entry that covers `bytes` / `rows`
+__device__ __forceinline__ int map_width_index(int bytes)
+{
+    return bytes <= 512 ? (bytes + 63) / 64 - 1 : 7 + (bytes - 512 + 127) / 128;
+}
+__device__ __forceinline__ int map_height_index(int rows)
+{
+    return rows <= 8 ? rows - 1 : (rows <= 16 ? 8 + (rows - 9) / 2 : 12 + (rows - 17) / 4);
+}
 
 struct WarpFastMaps {
     CUtensorMap m[kMapWCount * kMapHCount];
@@ -144,7 +163,12 @@ struct BoxPlan {
     int n_boxes;
     int x;                  // first column, in uint32 elements
     int y0;                 // first source row of the box
-    uint32_t bytes;         // sum of the box sizes (the mbarrier's transaction count)
+    uint32_t bytes;         // sum of the box sizes (the mbarrier's transaction count per frame)
+    int frame0, frame_step; // source frame of the item's frame i = frame0 + i * frame_step
+    int src_h;
+    int n_frames, fps;      // frames of the item / per ring stage
+    uint32_t ring, full0;   // shared-memory addresses: ring, first barrier of the set in use
+    uint32_t stride, frame_bytes, pitch;  // bytes per stage / staged frame / staged row
     int map_idx[kMaxBoxes];
     int row[kMaxBoxes];     // row offset of each box inside the stage
 };
@@ -181,60 +205,74 @@ __device__ __forceinline__ uint32_t lerp_pixel(const Pix &q, uint32_t r0, uint32
     return prmt(prmt(t0, t1, 0x4462u), t2, 0x7610u);
 }
 
+// The consumers' loop state (kept small so that the frame loop fits 64 registers); the elected
+// producer lane reads what it needs from the BoxPlan in shared memory.
 struct LoopCtx {
-    uint32_t ring, full0, empty0;  // shared-memory addresses of the ring / first barrier of the set
-    uint32_t stride;               // bytes per stage
+    uint32_t ring, full0;          // shared-memory addresses of the ring / first barrier of the set
+    uint32_t stride;               // bytes per stage (fps frames)
+    uint32_t frame_bytes;          // bytes per staged frame
     uint32_t pitch;                // bytes per staged row
+    int fps;                       // frames per stage
     int n_frames;
-    int frame0, frame_step;        // source / dst frame index of loop iteration i = frame0 + i * step
-    int src_h;
     const WarpFastMaps *maps;
     const BoxPlan *plan;           // in shared memory
 };
 
-// Elected thread: pull frame `i` of the item towards the SM.  TO_SMEM starts the copy into its
-// ring slot (`use` is the running count of stages this CTA has pushed through the barrier set);
-// otherwise the boxes are only prefetched into L2, kPrefetchAhead frames ahead of the ring, so
-// that the later copy does not wait on HBM.
+// Elected thread: pull the stage that starts at frame i0 of the item towards the SM.  TO_SMEM
+// starts the copies into its ring slot (`use` is the running count of stages this CTA has pushed
+// through the barrier set); otherwise the boxes are only prefetched into L2 so that the later
+// copy does not wait on HBM (used by depth-2 rings, whose copies run just one stage ahead).
+// Deliberately not inlined: it runs in one lane of one warp per stage and must not cost the
+// frame loop registers.
 template <int SLOG, bool TO_SMEM>
-__device__ __forceinline__ void produce(const LoopCtx &c, int i, uint32_t use)
+__device__ __noinline__ void produce(const BoxPlan *plan, const WarpFastMaps *maps, int i0,
+                                     uint32_t use)
 {
-    const int y = (c.frame0 + i * c.frame_step) * c.src_h + c.plan->y0;
-    const int nb = c.plan->n_boxes;
+    const BoxPlan &pl = *plan;
+    const int nf = min(pl.fps, pl.n_frames - i0);
+    const int nb = pl.n_boxes;
+    int y = (pl.frame0 + i0 * pl.frame_step) * pl.src_h + pl.y0;
+    const int y_step = pl.frame_step * pl.src_h;
     if (TO_SMEM) {
         const uint32_t slot = use & ((1u << SLOG) - 1u);
+        const uint32_t fb = pl.full0 + 8 * slot;
         // k-th fill of a slot waits for the (k-1)-th release; the first passes at once
-        mbar_wait(c.empty0 + 8 * slot, ((use >> SLOG) & 1u) ^ 1u);
-        const uint32_t fb = c.full0 + 8 * slot;
-        mbar_expect_tx(fb, c.plan->bytes);
-        const uint32_t sdst = c.ring + slot * c.stride;
+        mbar_wait(fb + (8u << SLOG), ((use >> SLOG) & 1u) ^ 1u);
+        mbar_expect_tx(fb, pl.bytes * nf);
+        uint32_t sdst = pl.ring + slot * pl.stride;
 #pragma unroll 1
-        for (int b = 0; b < nb; ++b)
-            tma_box_g2s(sdst + c.plan->row[b] * c.pitch, &c.maps->m[c.plan->map_idx[b]], c.plan->x,
-                        y + c.plan->row[b], fb);
+        for (int f = 0; f < nf; ++f, sdst += pl.frame_bytes, y += y_step)
+#pragma unroll 1
+            for (int b = 0; b < nb; ++b)
+                tma_box_g2s(sdst + pl.row[b] * pl.pitch, &maps->m[pl.map_idx[b]], pl.x,
+                            y + pl.row[b], fb);
     } else {
 #pragma unroll 1
-        for (int b = 0; b < nb; ++b)
-            tma_box_prefetch(&c.maps->m[c.plan->map_idx[b]], c.plan->x, y + c.plan->row[b]);
+        for (int f = 0; f < nf; ++f, y += y_step)
+#pragma unroll 1
+            for (int b = 0; b < nb; ++b)
+                tma_box_prefetch(&maps->m[pl.map_idx[b]], pl.x, y + pl.row[b]);
     }
 }
 
-// Iteration i of the frame loop: keep the ring and the L2 prefetch window full.  The producer role
-// rotates over the warps (one elected lane each) so that no warp is slower than the others --
-// a fixed producer warp paces the whole CTA, because every warp waits on the stages it issues.
+// Keep the ring (and, for depth-2 rings, the L2 prefetch window) full.  `done` = frames of the
+// item consumed up to and including the current stage.  The producer role rotates over the warps
+// (one elected lane each) so that no warp is slower than the others -- a fixed producer warp
+// paces the whole CTA, because every warp waits on the stages it issues.
 template <int SLOG>
-__device__ __forceinline__ void feed(const LoopCtx &c, int i, uint32_t use, int lane, int warp)
+__device__ __forceinline__ void feed(const LoopCtx &c, int done, uint32_t use, int lane, int warp)
 {
     constexpr int ahead = 1 << (SLOG - 1);
     if (lane != 0) return;
-    const int turn = (i - warp) & (kWarps - 1);
-    if (turn == 0 && i + ahead < c.n_frames) produce<SLOG, true>(c, i + ahead, use + ahead);
-    if (turn == kWarps / 2 && i + ahead + kPrefetchAhead < c.n_frames)
-        produce<SLOG, false>(c, i + ahead + kPrefetchAhead, 0);
+    const int turn = ((int)use - warp) & (kWarps - 1);
+    const int i_load = done + (ahead - 1) * c.fps;  // first frame of the stage `ahead` stages on
+    if (turn == 0 && i_load < c.n_frames) produce<SLOG, true>(c.plan, c.maps, i_load, use + ahead);
+    if (SLOG == 1 && turn == kWarps / 2 && i_load + kPrefetchAhead * c.fps < c.n_frames)
+        produce<SLOG, false>(c.plan, c.maps, i_load + kPrefetchAhead * c.fps, 0);
 }
 
 // The frame loop of a staged item.  FULL: every pixel of the tile is inside the dst image.
-// Ring depth 2^SLOG.  Returns the advanced stage counter.
+// Ring depth 2^SLOG stages of c.fps frames each.  Returns the advanced stage counter.
 template <bool LINEAR, bool FULL, int SLOG>
 __device__ __forceinline__ uint32_t frame_loop(const LoopCtx &c, const Pix (&px)[4], uint32_t use,
                                                uint8_t *d, const uint32_t d_step,
@@ -242,59 +280,71 @@ __device__ __forceinline__ uint32_t frame_loop(const LoopCtx &c, const Pix (&px)
                                                const uint32_t sel_pack, const int tid)
 {
     constexpr uint32_t smask = (1u << SLOG) - 1u;
-    // Frames in flight besides the one being consumed: half the ring.  The other half is slack
-    // between the warps -- a slot is refilled S/2 frames after its last use, so the refilling lane
+    // Stages in flight besides the one being consumed: half the ring.  The other half is slack
+    // between the warps -- a slot is refilled S/2 stages after its last use, so the refilling lane
     // practically never waits for a slower warp to release it.
     constexpr int ahead = 1 << (SLOG - 1);
     const int lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
-        for (int i = 0; i < ahead && i < c.n_frames; ++i) produce<SLOG, true>(c, i, use + i);
-        for (int i = ahead; i < ahead + kPrefetchAhead && i < c.n_frames; ++i)
-            produce<SLOG, false>(c, i, 0);
+        for (int st = 0; st < ahead && st * c.fps < c.n_frames; ++st)
+            produce<SLOG, true>(c.plan, c.maps, st * c.fps, use + st);
+        if (SLOG == 1)
+            for (int st = ahead; st < ahead + kPrefetchAhead && st * c.fps < c.n_frames; ++st)
+                produce<SLOG, false>(c.plan, c.maps, st * c.fps, 0);
     }
 
+    int done = 0;
 #pragma unroll 1
-    for (int i = 0; i < c.n_frames; ++i, d += d_step) {
+    while (done < c.n_frames) {
         const uint32_t slot = use & smask;
-        mbar_wait(c.full0 + 8 * slot, (use >> SLOG) & 1u);
-        const uint32_t sa = c.ring + slot * c.stride;  // row 0 of the windows
-        const uint32_t sb = sa + c.pitch;              // row 1
-        uint32_t P[4];
-        if (LINEAR) {
+        const uint32_t fb = c.full0 + 8 * slot;
+        mbar_wait(fb, (use >> SLOG) & 1u);
+        uint32_t sa = c.ring + slot * c.stride;  // row 0 of the windows, first frame of the stage
+        int nf = min(c.fps, c.n_frames - done);
+        done += nf;
+#pragma unroll 1
+        for (; nf > 0; --nf, sa += c.frame_bytes, d += d_step) {
+            const uint32_t sb = sa + c.pitch;  // row 1
+            uint32_t P[4];
+            if (LINEAR) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t a = px[k].addr + sa, b = px[k].addr + sb;
-                const uint32_t r0 = lds32(a), r1 = lds32(a + 4), r2 = lds32(a + 8);
-                const uint32_t s0 = lds32(b), s1 = lds32(b + 4), s2 = lds32(b + 8);
-                if (k == 3) {
-                    // all shared-memory reads of this stage are issued: hand the slot back early
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(c.empty0 + 8 * slot);
-                    feed<SLOG>(c, i, use, lane, warp);
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t a = px[k].addr + sa, b = px[k].addr + sb;
+                    const uint32_t r0 = lds32(a), r1 = lds32(a + 4), r2 = lds32(a + 8);
+                    const uint32_t s0 = lds32(b), s1 = lds32(b + 4), s2 = lds32(b + 8);
+                    if (k == 3 && nf == 1) {
+                        // every shared-memory read of this stage is issued: hand the slot back
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(fb + (8u << SLOG));
+                        feed<SLOG>(c, done, use, lane, warp);
+                    }
+                    P[k] = lerp_pixel(px[k], r0, r1, r2, s0, s1, s2);
                 }
-                P[k] = lerp_pixel(px[k], r0, r1, r2, s0, s1, s2);
+            } else {
+                uint32_t w[4][2];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    w[k][0] = lds32(px[k].addr + sa);
+                    w[k][1] = lds32(px[k].addr + sa + 4);
+                }
+                if (nf == 1) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(fb + (8u << SLOG));
+                    feed<SLOG>(c, done, use, lane, warp);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    P[k] = __funnelshift_r(w[k][0], w[k][1], px[k].sh) & px[k].w03;
             }
-        } else {
-            uint32_t w[4][2];
+            // pack 4 lanes x 3 bytes into 3 words and store 96-byte segments
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                w[k][0] = lds32(px[k].addr + sa);
-                w[k][1] = lds32(px[k].addr + sa + 4);
+                const uint32_t word = prmt(P[k], __shfl_down_sync(0xffffffffu, P[k], 1), sel_pack);
+                if (FULL ? lane_st : seg_ok[k])
+                    st_stream(reinterpret_cast<uint32_t *>(d + 96 * k), word);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(c.empty0 + 8 * slot);
-            feed<SLOG>(c, i, use, lane, warp);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                P[k] = __funnelshift_r(w[k][0], w[k][1], px[k].sh) & px[k].w03;
         }
         ++use;
-        // pack 4 lanes x 3 bytes into 3 words and store 96-byte segments
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t word = prmt(P[k], __shfl_down_sync(0xffffffffu, P[k], 1), sel_pack);
-            if (FULL ? lane_st : seg_ok[k]) st_stream(reinterpret_cast<uint32_t *>(d + 96 * k), word);
-        }
     }
     return use;
 }
@@ -311,8 +361,9 @@ __device__ __forceinline__ uint32_t frame_loop_any(const bool full_tile, const L
     return frame_loop<LINEAR, false, SLOG>(c, px, use, d, d_step, lane_st, seg_ok, sel_pack, tid);
 }
 
-template <bool LINEAR>
-__global__ void __launch_bounds__(kThreads, 4)
+// MINB = CTAs per SM the register allocation is bounded for (4 -> 64 registers, 3 -> 80).
+template <bool LINEAR, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
                       const __grid_constant__ WarpFastMaps maps,
                       const __grid_constant__ ChunkPlan plan, const int tiles_x, const int tiles_y,
@@ -432,40 +483,39 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
         by0 = s_box[2];
         by1 = s_box[3];
 
-        // staged geometry: 16-byte aligned first column, width rounded to the tensor-map menu
+        // staged geometry: 16-byte aligned first column, box shapes from the tensor-map menu
         const int a0 = (3 * bx0) & ~15;
         const int need_w = ((3 * (bx1 + 1) + 15) & ~15) - a0;
-        const int pitch = (need_w + kMapWStep - 1) / kMapWStep * kMapWStep;
+        const int wi = map_width_index(need_w);
+        const int pitch = map_width(wi);
         const int nrows = by1 - by0 + 1;
-        bool staged = any && pitch <= kMapWStep * kMapWCount && nrows <= 128;
+        bool staged = any && need_w <= kMaxBoxWidth && nrows <= kMaxBoxes * kMaxBoxHeight;
         if (tid == 0 && staged) {
-            // cover the rows with at most kMaxBoxes boxes of power-of-two height, largest first
             int rem = nrows, row = 0, nb = 0;
             while (rem > 0) {
-                int h = 1 << (31 - __clz(rem));
-                const int up = (h == rem) ? h : 2 * h;
-                if (nb == kMaxBoxes - 1 || up - rem <= max(1, rem >> 3)) h = up;
-                h = min(h, 1 << (kMapHCount - 1));
-                if (nb == kMaxBoxes) {
-                    nb = 0;  // does not fit the plan: not staged
-                    break;
-                }
-                s_plan.map_idx[nb] = (pitch / kMapWStep - 1) * kMapHCount + (31 - __clz(h));
+                const int hi = map_height_index(min(rem, kMaxBoxHeight));
+                s_plan.map_idx[nb] = wi * kMapHCount + hi;
                 s_plan.row[nb] = row;
-                row += h;
-                rem -= h;
+                row += map_height(hi);
+                rem -= map_height(hi);
                 ++nb;
             }
             s_plan.n_boxes = nb;
             s_plan.x = a0 >> 2;
             s_plan.y0 = by0;
             s_plan.bytes = (uint32_t)row * (uint32_t)pitch;
+            s_plan.frame0 = g_first + f0 * g_stride;
+            s_plan.frame_step = g_stride;
+            s_plan.src_h = p.src_h;
         }
         __syncthreads();  // s_plan visible; s_box / s_any may be re-initialised by the next item
-        staged = staged && s_plan.n_boxes > 0;
-        const uint32_t stage_bytes = staged ? s_plan.bytes : 0u;
-        const int stage_stride = (int)((stage_bytes + 127u) & ~127u);
-        staged = staged && stage_bytes <= (uint32_t)ring_bytes / 2;
+        const uint32_t frame_bytes = staged ? ((s_plan.bytes + 127u) & ~127u) : 0u;
+        staged = staged && 2 * frame_bytes <= (uint32_t)ring_bytes;
+        // frames per stage: as many as still leave a ring of 4 stages
+        const int fps = (4 * kMaxStageFrames * frame_bytes <= (uint32_t)ring_bytes)
+                            ? kMaxStageFrames
+                            : (8 * frame_bytes <= (uint32_t)ring_bytes ? 2 : 1);
+        const int stage_stride = fps * (int)frame_bytes;
         const int slog = (8 * stage_stride <= ring_bytes) ? 3 : (4 * stage_stride <= ring_bytes ? 2 : 1);
 
         // ---- store geometry ---------------------------------------------------------------------
@@ -517,19 +567,26 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
             }
             LoopCtx c;
             c.ring = ring;
-            c.full0 = bar0 + 16 * (1 << slog) - 32;
-            c.empty0 = c.full0 + 8 * (1 << slog);
+            c.full0 = bar0 + 16 * (1 << slog) - 32;  // the set's empty[] barriers follow its full[]
             c.stride = stage_stride;
+            c.frame_bytes = frame_bytes;
             c.pitch = pitch;
+            c.fps = fps;
             c.n_frames = n_frames;
-            c.frame0 = g_first + f0 * g_stride;
-            c.frame_step = g_stride;
-            c.src_h = p.src_h;
             c.maps = &maps;
             c.plan = &s_plan;
             keep(c.ring);
             keep(c.full0);
-            keep(c.empty0);
+            if (tid == 0) {
+                s_plan.n_frames = n_frames;
+                s_plan.fps = fps;
+                s_plan.ring = c.ring;
+                s_plan.full0 = c.full0;
+                s_plan.stride = c.stride;
+                s_plan.frame_bytes = c.frame_bytes;
+                s_plan.pitch = c.pitch;
+            }
+            __syncthreads();
             // every thread tracks the counter in a register; thread 0 publishes it for the next item
             uint32_t use = s_use[slog - 1];
             if (slog == 3)
@@ -627,7 +684,7 @@ int get_maps(const void *base, int row_bytes, long long rows, WarpFastMaps &out)
     const cuuint32_t estride[2] = {1, 1};
     for (int wi = 0; wi < kMapWCount; ++wi)
         for (int hi = 0; hi < kMapHCount; ++hi) {
-            const cuuint32_t box[2] = {(cuuint32_t)((wi + 1) * kMapWStep / 4), (cuuint32_t)(1u << hi)};
+            const cuuint32_t box[2] = {(cuuint32_t)(map_width(wi) / 4), (cuuint32_t)map_height(hi)};
             CUresult r = g_encode(&victim->maps.m[wi * kMapHCount + hi], CU_TENSOR_MAP_DATA_TYPE_UINT32,
                                   2, const_cast<void *>(base), gdim, gstride, box, estride,
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -652,17 +709,28 @@ struct KernelConfig {
     int ctas_per_sm = 0;
     int ring_bytes = 0;
 };
-KernelConfig g_cfg[2];
+KernelConfig g_cfg[2][2];  // [linear][MINB - 3]
 
-template <bool LINEAR> int configure(KernelConfig &cfg)
+// BEVK_FAST_CTAS=3|4 picks the register / occupancy variant (tuning aid); default below.
+int fast_min_ctas()
 {
-    auto kern = warp_fast_u8c3_kernel<LINEAR>;
+    static int v = 0;
+    if (!v) {
+        const char *e = getenv("BEVK_FAST_CTAS");
+        v = (e && (e[0] == '3' || e[0] == '4')) ? e[0] - '0' : 3;
+    }
+    return v;
+}
+
+template <bool LINEAR, int MINB> int configure(KernelConfig &cfg)
+{
+    auto kern = warp_fast_u8c3_kernel<LINEAR, MINB>;
     // how many CTAs the register file allows, then split the shared memory evenly between them
     BEVK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1024));
     int by_regs = 0;
     BEVK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&by_regs, kern, kThreads, 16 * 1024));
     if (by_regs < 1) BEVK_FAIL(BEVK_E_CUDA, "staged warp kernel does not fit an SM");
-    by_regs = by_regs > 4 ? 4 : by_regs;
+    by_regs = by_regs > MINB ? MINB : by_regs;
     int dev = 0, smem_sm = 0;
     BEVK_CUDA(cudaGetDevice(&dev));
     BEVK_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
@@ -678,6 +746,14 @@ template <bool LINEAR> int configure(KernelConfig &cfg)
     return BEVK_OK;
 }
 
+template <bool LINEAR, int MINB>
+void launch(int grid, int smem, cudaStream_t stream, const BevkWarpParams &p, const WarpFastMaps &maps,
+            const ChunkPlan &plan, int tiles_x, int tiles_y, int items, int ring_bytes, int *counter)
+{
+    warp_fast_u8c3_kernel<LINEAR, MINB><<<grid, kThreads, smem, stream>>>(
+        p, maps, plan, tiles_x, tiles_y, items, ring_bytes, counter);
+}
+
 }  // namespace
 
 int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, int linear,
@@ -691,9 +767,11 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
     if ((p_in.src_w * 3) % 16 != 0 || (p_in.dst_w % 4) != 0) return 0;
     if (((uintptr_t)p_in.src % 16) != 0 || ((uintptr_t)p_in.dst % 4) != 0) return 0;
 
-    KernelConfig &cfg = g_cfg[linear ? 1 : 0];
+    const int minb = fast_min_ctas();
+    KernelConfig &cfg = g_cfg[linear ? 1 : 0][minb - 3];
     if (!cfg.ready) {
-        int rc = linear ? configure<true>(cfg) : configure<false>(cfg);
+        int rc = linear ? (minb == 3 ? configure<true, 3>(cfg) : configure<true, 4>(cfg))
+                        : (minb == 3 ? configure<false, 3>(cfg) : configure<false, 4>(cfg));
         if (rc) return rc;
     }
 
@@ -758,12 +836,17 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
     if (counter) BEVK_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));
 
     const int smem = cfg.ring_bytes + kBarBytes + kTailSlack;
-    if (linear)
-        warp_fast_u8c3_kernel<true><<<grid, kThreads, smem, stream>>>(
-            p, maps, plan, tiles_x, tiles_y, (int)items, cfg.ring_bytes, counter);
-    else
-        warp_fast_u8c3_kernel<false><<<grid, kThreads, smem, stream>>>(
-            p, maps, plan, tiles_x, tiles_y, (int)items, cfg.ring_bytes, counter);
+    if (linear) {
+        if (minb == 3)
+            launch<true, 3>(grid, smem, stream, p, maps, plan, tiles_x, tiles_y, (int)items, cfg.ring_bytes, counter);
+        else
+            launch<true, 4>(grid, smem, stream, p, maps, plan, tiles_x, tiles_y, (int)items, cfg.ring_bytes, counter);
+    } else {
+        if (minb == 3)
+            launch<false, 3>(grid, smem, stream, p, maps, plan, tiles_x, tiles_y, (int)items, cfg.ring_bytes, counter);
+        else
+            launch<false, 4>(grid, smem, stream, p, maps, plan, tiles_x, tiles_y, (int)items, cfg.ring_bytes, counter);
+    }
     BEVK_CUDA(cudaGetLastError());
     return 1;
 }
