@@ -86,11 +86,11 @@ BEVK_HD int bevk_block_width(int dst_w, int dst_h)
     return bw0 > dst_w ? dst_w : bw0;
 }
 
-// Quantised source coordinate of dst pixel (x, y).  scale = 32 (bilinear, 1/32 px) or 1 (nearest).
-BEVK_HD void bevk_map_pixel(const double *M, int x, int y, int bw0, double scale, int &X, int &Y)
+// Quantised source coordinate of dst pixel (xb + x1, y), xb = start of its cv2 block column.
+// scale = 32 (bilinear, 1/32 px) or 1 (nearest).
+BEVK_HD void bevk_map_pixel_xb(const double *M, int xb, int x1, int y, double scale, int &X, int &Y)
 {
-    const int xb = (x / bw0) * bw0;
-    const double dxb = (double)xb, dx1 = (double)(x - xb), dy = (double)y;
+    const double dxb = (double)xb, dx1 = (double)x1, dy = (double)y;
     const double X0 = bevk_add(bevk_add(bevk_mul(M[0], dxb), bevk_mul(M[1], dy)), M[2]);
     const double Y0 = bevk_add(bevk_add(bevk_mul(M[3], dxb), bevk_mul(M[4], dy)), M[5]);
     const double W0 = bevk_add(bevk_add(bevk_mul(M[6], dxb), bevk_mul(M[7], dy)), M[8]);
@@ -98,6 +98,11 @@ BEVK_HD void bevk_map_pixel(const double *M, int x, int y, int bw0, double scale
     w = (w != 0.0) ? bevk_div(scale, w) : 0.0;
     X = bevk_round_sat(bevk_mul(bevk_add(X0, bevk_mul(M[0], dx1)), w));
     Y = bevk_round_sat(bevk_mul(bevk_add(Y0, bevk_mul(M[3], dx1)), w));
+}
+BEVK_HD void bevk_map_pixel(const double *M, int x, int y, int bw0, double scale, int &X, int &Y)
+{
+    const int xb = (x / bw0) * bw0;
+    bevk_map_pixel_xb(M, xb, x - xb, y, scale, X, Y);
 }
 
 // ----------------------------------------------------------------------------- warp launch plan

@@ -161,7 +161,7 @@ __device__ __forceinline__ void window(int s, int frac, int n, int &first, int &
 // What the elected producer thread needs to fetch one frame's bounding box.
 struct BoxPlan {
     int n_boxes;
-    int x;                  // first column, in uint32 elements
+    int x;                  // first column, in uint32 elements (TMA wants 16-byte aligned box rows)
     int y0;                 // first source row of the box
     uint32_t bytes;         // sum of the box sizes (the mbarrier's transaction count per frame)
     int frame0, frame_step; // source frame of the item's frame i = frame0 + i * frame_step
@@ -171,6 +171,14 @@ struct BoxPlan {
     uint32_t stride, frame_bytes, pitch;  // bytes per stage / staged frame / staged row
     int map_idx[kMaxBoxes];
     int row[kMaxBoxes];     // row offset of each box inside the stage
+};
+
+// A decoded work item (thread 0 decodes the next one while the CTA works on the current one).
+struct ItemDesc {
+    int item;                 // >= total_items: no more work
+    int gi, tile_x, tile_y;   // homography group, tile position
+    int f0, n_frames;         // frames [f0, f0 + n_frames) of the group's run
+    int first, stride;        // the run: frame index = first + f * stride
 };
 
 // Frame-invariant description of one dst pixel.
@@ -184,12 +192,11 @@ struct Pix {
 };
 
 // One pixel out of its staged window: cv2's fixed-point bilinear, result [c0, c1, c2, 0].
-__device__ __forceinline__ uint32_t lerp_pixel(const Pix &q, uint32_t r0, uint32_t r1, uint32_t r2,
-                                               uint32_t s0, uint32_t s1, uint32_t s2)
+// f0 / g0 = window bytes 0..3 of row 0 / 1, f1 / g1 = window bytes 4.. (already byte-aligned).
+__device__ __forceinline__ uint32_t lerp_aligned(const Pix &q, uint32_t f0, uint32_t f1, uint32_t g0,
+                                                 uint32_t g1)
 {
-    // byte-align the window of both rows: F = [B0 B1 B2 B3], G = [B1 B4 B2 B5]
-    const uint32_t f0 = __funnelshift_r(r0, r1, q.sh), f1 = __funnelshift_r(r1, r2, q.sh);
-    const uint32_t g0 = __funnelshift_r(s0, s1, q.sh), g1 = __funnelshift_r(s1, s2, q.sh);
+    // F = [B0 B1 B2 B3], G = [B1 B4 B2 B5]
     const uint32_t fg = prmt(f0, f1, 0x5241u), gg = prmt(g0, g1, 0x5241u);
     // horizontal pass: h[row][channel] = a0 * tap0 + a1 * tap1
     const uint32_t h00 = __dp4a(f0, q.w03, 0u);
@@ -271,13 +278,13 @@ __device__ __forceinline__ void feed(const LoopCtx &c, int done, uint32_t use, i
         produce<SLOG, false>(c.plan, c.maps, i_load + kPrefetchAhead * c.fps, 0);
 }
 
-// The frame loop of a staged item.  FULL: every pixel of the tile is inside the dst image.
-// Ring depth 2^SLOG stages of c.fps frames each.  Returns the advanced stage counter.
-template <bool LINEAR, bool FULL, int SLOG>
+// The frame loop of a staged item.  Ring depth 2^SLOG stages of c.fps frames each.  Returns the
+// advanced stage counter.
+template <bool LINEAR, int SLOG>
 __device__ __forceinline__ uint32_t frame_loop(const LoopCtx &c, const Pix (&px)[4], uint32_t use,
                                                uint8_t *d, const uint32_t d_step,
-                                               const bool lane_st, const bool (&seg_ok)[4],
-                                               const uint32_t sel_pack, const int tid)
+                                               const bool (&seg_ok)[4], const uint32_t sel_pack,
+                                               const int tid)
 {
     constexpr uint32_t smask = (1u << SLOG) - 1u;
     // Stages in flight besides the one being consumed: half the ring.  The other half is slack
@@ -318,7 +325,10 @@ __device__ __forceinline__ uint32_t frame_loop(const LoopCtx &c, const Pix (&px)
                         if (lane == 0) mbar_arrive(fb + (8u << SLOG));
                         feed<SLOG>(c, done, use, lane, warp);
                     }
-                    P[k] = lerp_pixel(px[k], r0, r1, r2, s0, s1, s2);
+                    // byte-align the window of both rows
+                    const uint32_t sh = px[k].sh;
+                    P[k] = lerp_aligned(px[k], __funnelshift_r(r0, r1, sh), __funnelshift_r(r1, r2, sh),
+                                        __funnelshift_r(s0, s1, sh), __funnelshift_r(s1, s2, sh));
                 }
             } else {
                 uint32_t w[4][2];
@@ -340,25 +350,13 @@ __device__ __forceinline__ uint32_t frame_loop(const LoopCtx &c, const Pix (&px)
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const uint32_t word = prmt(P[k], __shfl_down_sync(0xffffffffu, P[k], 1), sel_pack);
-                if (FULL ? lane_st : seg_ok[k])
+                if (seg_ok[k])
                     st_stream(reinterpret_cast<uint32_t *>(d + 96 * k), word);
             }
         }
         ++use;
     }
     return use;
-}
-
-template <bool LINEAR, int SLOG>
-__device__ __forceinline__ uint32_t frame_loop_any(const bool full_tile, const LoopCtx &c,
-                                                   const Pix (&px)[4], uint32_t use, uint8_t *d,
-                                                   const uint32_t d_step, const bool lane_st,
-                                                   const bool (&seg_ok)[4], const uint32_t sel_pack,
-                                                   const int tid)
-{
-    if (full_tile)
-        return frame_loop<LINEAR, true, SLOG>(c, px, use, d, d_step, lane_st, seg_ok, sel_pack, tid);
-    return frame_loop<LINEAR, false, SLOG>(c, px, use, d, d_step, lane_st, seg_ok, sel_pack, tid);
 }
 
 // MINB = CTAs per SM the register allocation is bounded for (4 -> 64 registers, 3 -> 80).
@@ -377,7 +375,8 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
     __shared__ int s_box[4];
     __shared__ int s_any;
     __shared__ uint32_t s_use[3];
-    __shared__ int s_next;
+    __shared__ ItemDesc s_item[2];  // current / next work item, decoded by thread 0
+    __shared__ double s_M[BEVK_MAX_GROUPS][9];
     __shared__ BoxPlan s_plan;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -403,20 +402,44 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
 
     // Items are (chunk, group, tile) with the chunk index slowest: long chunks first.  The first
     // gridDim.x items are taken by block index, the rest are pulled from *next_item.
+    // Items are (chunk, group, tile) with the chunk index slowest: long chunks first.  The first
+    // gridDim.x items are taken by block index, the rest are pulled from *next_item.  Thread 0
+    // decodes an item (integer divisions, parameter reads) one item ahead of its use.
     const int per_chunk = p.n_groups * n_tiles;
-    int item = blockIdx.x;
-#pragma unroll 1
-    while (item < total_items) {
+    auto decode = [&](int item, ItemDesc &o) {
+        o.item = item;
+        if (item >= total_items) return;
         const int chunk = item / per_chunk, rem = item - chunk * per_chunk;
         const int gi = rem / n_tiles, tile = rem - gi * n_tiles;
-        const int g_first = p.g[gi].first, g_stride = p.g[gi].stride, g_count = p.g[gi].count;
         // column-major walk: concurrently running CTAs cover whole tile columns, i.e. both the
         // magnified far field (store-heavy) and the minified near field (load-heavy)
-        const int tile_x = tile / tiles_y, tile_y = tile - tile_x * tiles_y;
-        const int f0 = (int)(((unsigned long long)g_count * plan.cum[chunk]) >> 16);
-        const int n_frames = (int)(((unsigned long long)g_count * plan.cum[chunk + 1]) >> 16) - f0;
+        o.gi = gi;
+        o.tile_x = tile / tiles_y;
+        o.tile_y = tile - o.tile_x * tiles_y;
+        const int count = p.g[gi].count;
+        o.f0 = (int)(((unsigned long long)count * plan.cum[chunk]) >> 16);
+        o.n_frames = (int)(((unsigned long long)count * plan.cum[chunk + 1]) >> 16) - o.f0;
+        o.first = p.g[gi].first;
+        o.stride = p.g[gi].stride;
+    };
+    for (int i = tid; i < p.n_groups * 9; i += kThreads) s_M[i / 9][i % 9] = p.g[i / 9].M[i % 9];
+    if (tid == 0) decode(blockIdx.x, s_item[0]);
+    __syncthreads();
+    const bool bw0_pow2 = (p.bw0 & (p.bw0 - 1)) == 0;
+
+    int par = 0;
+#pragma unroll 1
+    while (true) {
+        const int item = s_item[par].item;
+        if (item >= total_items) break;
+        const int gi = s_item[par].gi, tile_x = s_item[par].tile_x, tile_y = s_item[par].tile_y;
+        const int f0 = s_item[par].f0, n_frames = s_item[par].n_frames;
+        const int g_first = s_item[par].first, g_stride = s_item[par].stride;
         const int x0 = tile_x * kTileW, y = tile_y * kTileH + warp;
-        if (tid == 0) s_next = next_item ? (int)gridDim.x + atomicAdd(next_item, 1) : item + (int)gridDim.x;
+        par ^= 1;
+        if (tid == 0)
+            decode(next_item ? (int)gridDim.x + atomicAdd(next_item, 1) : item + (int)gridDim.x,
+                   s_item[par]);
 
         // ---- 1. set-up ------------------------------------------------------------------------
         if (tid == 0) {
@@ -435,8 +458,9 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
             const int x = x0 + lane + 32 * k;
             const bool in_dst = (x < p.dst_w) && (y < p.dst_h);
             int X, Y;
-            bevk_map_pixel(p.g[gi].M, min(x, p.dst_w - 1), min(y, p.dst_h - 1), p.bw0,
-                           LINEAR ? 32.0 : 1.0, X, Y);
+            const int xc = min(x, p.dst_w - 1);
+            const int xb = bw0_pow2 ? (xc & ~(p.bw0 - 1)) : (xc / p.bw0) * p.bw0;
+            bevk_map_pixel_xb(s_M[gi], xb, xc - xb, min(y, p.dst_h - 1), LINEAR ? 32.0 : 1.0, X, Y);
             if (LINEAR) {
                 const int sx = bevk_sat16(X >> 5), sy = bevk_sat16(Y >> 5);
                 window(sx, X & 31, p.src_w, cs[k], wc0[k], wc1[k]);
@@ -461,13 +485,10 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
                 by1 = max(by1, rs[k] + (LINEAR ? 1 : 0));
             }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            bx0 = min(bx0, __shfl_xor_sync(0xffffffffu, bx0, o));
-            bx1 = max(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
-            by0 = min(by0, __shfl_xor_sync(0xffffffffu, by0, o));
-            by1 = max(by1, __shfl_xor_sync(0xffffffffu, by1, o));
-        }
+        bx0 = __reduce_min_sync(0xffffffffu, bx0);
+        bx1 = __reduce_max_sync(0xffffffffu, bx1);
+        by0 = __reduce_min_sync(0xffffffffu, by0);
+        by1 = __reduce_max_sync(0xffffffffu, by1);
         if (lane == 0 && bx1 >= 0) {
             atomicMin(&s_box[0], bx0);
             atomicMax(&s_box[1], bx1);
@@ -477,7 +498,6 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
         }
         __syncthreads();
         const bool any = s_any != 0;
-        item = s_next;
         bx0 = s_box[0];
         bx1 = s_box[1];
         by0 = s_box[2];
@@ -525,12 +545,10 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
         const uint32_t sel_pack = r4 == 0 ? 0x4210u : (r4 == 1 ? 0x5421u : 0x6542u);
         const bool lane_st = r4 < 3;
         bool seg_ok[4];
-        bool full_tile = (y < p.dst_h);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int valid_px = min(32, p.dst_w - (x0 + 32 * k));  // multiple of 4 (dst_w % 4 == 0)
             seg_ok[k] = (y < p.dst_h) && lane_st && (4 * q < valid_px);
-            full_tile = full_tile && valid_px == 32;
         }
         uint32_t d_step = (uint32_t)g_stride * (uint32_t)p.dst_frame_elems;  // < 2^32 (host check)
         keep(d_step);
@@ -590,11 +608,11 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
             // every thread tracks the counter in a register; thread 0 publishes it for the next item
             uint32_t use = s_use[slog - 1];
             if (slog == 3)
-                use = frame_loop_any<LINEAR, 3>(full_tile, c, px, use, d, d_step, lane_st, seg_ok, sel_pack, tid);
+                use = frame_loop<LINEAR, 3>(c, px, use, d, d_step, seg_ok, sel_pack, tid);
             else if (slog == 2)
-                use = frame_loop_any<LINEAR, 2>(full_tile, c, px, use, d, d_step, lane_st, seg_ok, sel_pack, tid);
+                use = frame_loop<LINEAR, 2>(c, px, use, d, d_step, seg_ok, sel_pack, tid);
             else
-                use = frame_loop_any<LINEAR, 1>(full_tile, c, px, use, d, d_step, lane_st, seg_ok, sel_pack, tid);
+                use = frame_loop<LINEAR, 1>(c, px, use, d, d_step, seg_ok, sel_pack, tid);
             __syncthreads();  // every warp has read s_use and left the ring
             if (tid == 0) s_use[slog - 1] = use;
         } else {
@@ -679,12 +697,16 @@ int get_maps(const void *base, int row_bytes, long long rows, WarpFastMaps &out)
         }
         if (e.stamp < victim->stamp) victim = &e;
     }
-    const cuuint64_t gdim[2] = {(cuuint64_t)(row_bytes / 4), (cuuint64_t)rows};
     const cuuint64_t gstride[1] = {(cuuint64_t)row_bytes};
     const cuuint32_t estride[2] = {1, 1};
     for (int wi = 0; wi < kMapWCount; ++wi)
         for (int hi = 0; hi < kMapHCount; ++hi) {
-            const cuuint32_t box[2] = {(cuuint32_t)(map_width(wi) / 4), (cuuint32_t)map_height(hi)};
+            // uint32 elements: up to 256 per box row = 1024 bytes; every box row starts 16-byte
+            // aligned in global memory, which the TMA unit requires (a start on another byte
+            // raises an illegal-instruction fault -- tried for a 2-byte shifted second copy)
+            const int es = 4;
+            const cuuint64_t gdim[2] = {(cuuint64_t)(row_bytes / es), (cuuint64_t)rows};
+            const cuuint32_t box[2] = {(cuuint32_t)(map_width(wi) / es), (cuuint32_t)map_height(hi)};
             CUresult r = g_encode(&victim->maps.m[wi * kMapHCount + hi], CU_TENSOR_MAP_DATA_TYPE_UINT32,
                                   2, const_cast<void *>(base), gdim, gstride, box, estride,
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -693,7 +715,7 @@ int get_maps(const void *base, int row_bytes, long long rows, WarpFastMaps &out)
             if (r != CUDA_SUCCESS) {
                 victim->base = nullptr;
                 BEVK_FAIL(BEVK_E_CUDA, "cuTensorMapEncodeTiled failed (code %d) for a %ux%u box",
-                          (int)r, box[0] * 4, box[1]);
+                          (int)r, box[0] * es, box[1]);
             }
         }
     victim->base = base;
@@ -735,7 +757,9 @@ template <bool LINEAR, int MINB> int configure(KernelConfig &cfg)
     BEVK_CUDA(cudaGetDevice(&dev));
     BEVK_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
     // per CTA: 1 KB reserved by the driver + static shared memory
-    int ring = smem_sm / by_regs - 1024 - 512 - kBarBytes - kTailSlack;
+    cudaFuncAttributes attr;
+    BEVK_CUDA(cudaFuncGetAttributes(&attr, kern));
+    int ring = smem_sm / by_regs - 1024 - (int)attr.sharedSizeBytes - kBarBytes - kTailSlack;
     ring &= ~127;
     if (ring > 200 * 1024) ring = 200 * 1024;
     BEVK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
