@@ -307,9 +307,60 @@ def ours(args, wl):
             line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"],
                                     "kind": cb["kind"], "sample": cb["sample"], "cpu": cb["cpu"],
                                     "ms_per_frame": cb["ms_per_frame"]}
+        if world == 1 and not args.no_projection:
+            del frames, out
+            torch.cuda.empty_cache()
+            line["projection"] = projection_leg(dev, min(args.steps, 20), min(args.cpu_seconds, 5.0),
+                                                not args.no_cpu_baseline)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def projection_leg(dev, steps, cpu_seconds, with_cpu):
+    """BASELINE configs[2]: 10 M synthetic xywh-theta BEV boxes -> image corners and back (fp32),
+    through bev_b200.rbox_torch (one fused CUDA kernel per direction).  Returns the `projection`
+    object of the JSON line: projections/s (one box through one direction), the HBM roofline of
+    the two kernels (52 B per box and direction) and the reference's numpy float64
+    chain timed on a bounded sample of the same boxes."""
+    import torch
+    from bev_b200 import rbox_torch
+    n = 10_000_000
+    g = torch.Generator(device=dev).manual_seed(0)
+    u = torch.rand((n, 5), dtype=torch.float32, device=dev, generator=g)
+    lo = torch.tensor([0.0, 0.0, 4.0, 8.0, -np.pi], dtype=torch.float32, device=dev)
+    hi = torch.tensor([1024.0, 1024.0, 40.0, 120.0, np.pi], dtype=torch.float32, device=dev)
+    box = lo + u * (hi - lo)
+    del u
+    H_back = h_canon(1)             # image -> BEV
+    H_fwd = np.linalg.inv(H_back)   # BEV -> image
+    for _ in range(3):
+        img = rbox_torch.xywhr_to_img_corners(box, H_fwd, "bev")
+        back = rbox_torch.img_corners_to_xywhr(img, H_back, "bev")
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        img = rbox_torch.xywhr_to_img_corners(box, H_fwd, "bev")
+        back = rbox_torch.img_corners_to_xywhr(img, H_back, "bev")
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    peak, peak_src = measured_peak()
+    algo = 2 * 52 * n
+    out = {"metric": "rbox projections/s", "value": 2 * n / (ms * 1e-3) / 1e6, "unit": "Mproj/s",
+           "boxes": n, "ms_fwd_plus_back": ms, "dtype": "f32 io, f64 registers",
+           "gpu_launches_per_step": 2,
+           "roofline": {"bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "peak": peak,
+                        "unit": "GB/s", "frac": algo / (ms * 1e-3) / 1e9 / peak,
+                        "algo_bytes_per_step": algo, "peak_source": peak_src},
+           "round_trip_max_abs_err": float((back[:, :4] - box[:, :4]).abs().max().item())}
+    if with_cpu:
+        from oracle import ref_cpu
+        sample = box[:200_000].cpu().numpy()
+        cb = ref_cpu.time_rbox_chain(sample, H_fwd, H_back, "bev", min_seconds=cpu_seconds)
+        out["cpu_baseline"] = cb
+    return out
 
 
 def main():
@@ -324,6 +375,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling aid: skip the host-buffer leg")
+    ap.add_argument("--no-projection", action="store_true", help="skip the rbox projection leg")
     args = ap.parse_args()
 
     if args.impl == "reference":
