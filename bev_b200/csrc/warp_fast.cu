@@ -423,7 +423,12 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
         o.stride = p.g[gi].stride;
     };
     for (int i = tid; i < p.n_groups * 9; i += kThreads) s_M[i / 9][i % 9] = p.g[i / 9].M[i % 9];
-    if (tid == 0) decode(blockIdx.x, s_item[0]);
+    if (tid == 0) {
+        decode(blockIdx.x, s_item[0]);
+        s_box[0] = s_box[2] = 1 << 30;
+        s_box[1] = s_box[3] = -1;
+        s_any = 0;
+    }
     __syncthreads();
     const bool bw0_pow2 = (p.bw0 & (p.bw0 - 1)) == 0;
 
@@ -437,20 +442,8 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
         const int g_first = s_item[par].first, g_stride = s_item[par].stride;
         const int x0 = tile_x * kTileW, y = tile_y * kTileH + warp;
         par ^= 1;
-        if (tid == 0)
-            decode(next_item ? (int)gridDim.x + atomicAdd(next_item, 1) : item + (int)gridDim.x,
-                   s_item[par]);
 
         // ---- 1. set-up ------------------------------------------------------------------------
-        if (tid == 0) {
-            s_box[0] = 1 << 30;
-            s_box[1] = -1;
-            s_box[2] = 1 << 30;
-            s_box[3] = -1;
-            s_any = 0;
-        }
-        __syncthreads();
-
         int cs[4], rs[4], wc0[4], wc1[4], wr0[4], wr1[4];
         int bx0 = 1 << 30, bx1 = -1, by0 = 1 << 30, by1 = -1;
 #pragma unroll
@@ -510,26 +503,15 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
         const int pitch = map_width(wi);
         const int nrows = by1 - by0 + 1;
         bool staged = any && need_w <= kMaxBoxWidth && nrows <= kMaxBoxes * kMaxBoxHeight;
-        if (tid == 0 && staged) {
-            int rem = nrows, row = 0, nb = 0;
-            while (rem > 0) {
-                const int hi = map_height_index(min(rem, kMaxBoxHeight));
-                s_plan.map_idx[nb] = wi * kMapHCount + hi;
-                s_plan.row[nb] = row;
-                row += map_height(hi);
-                rem -= map_height(hi);
-                ++nb;
+        // rows the boxes cover: at most kMaxBoxes boxes, each the smallest menu height that fits
+        int box_rows = 0;
+        if (staged)
+            for (int rem = nrows; rem > 0;) {
+                const int h = map_height(map_height_index(min(rem, kMaxBoxHeight)));
+                box_rows += h;
+                rem -= h;
             }
-            s_plan.n_boxes = nb;
-            s_plan.x = a0 >> 2;
-            s_plan.y0 = by0;
-            s_plan.bytes = (uint32_t)row * (uint32_t)pitch;
-            s_plan.frame0 = g_first + f0 * g_stride;
-            s_plan.frame_step = g_stride;
-            s_plan.src_h = p.src_h;
-        }
-        __syncthreads();  // s_plan visible; s_box / s_any may be re-initialised by the next item
-        const uint32_t frame_bytes = staged ? ((s_plan.bytes + 127u) & ~127u) : 0u;
+        const uint32_t frame_bytes = ((uint32_t)(box_rows * pitch) + 127u) & ~127u;
         staged = staged && 2 * frame_bytes <= (uint32_t)ring_bytes;
         // frames per stage: as many as still leave a ring of 4 stages
         const int fps = (4 * kMaxStageFrames * frame_bytes <= (uint32_t)ring_bytes)
@@ -537,6 +519,43 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
                             : (8 * frame_bytes <= (uint32_t)ring_bytes ? 2 : 1);
         const int stage_stride = fps * (int)frame_bytes;
         const int slog = (8 * stage_stride <= ring_bytes) ? 3 : (4 * stage_stride <= ring_bytes ? 2 : 1);
+        const uint32_t full0 = bar0 + 16 * (1 << slog) - 32;  // the set's empty[] follow its full[]
+        if (tid == 0) {
+            if (staged) {
+                int rem = nrows, row = 0, nb = 0;
+                while (rem > 0) {
+                    const int hi = map_height_index(min(rem, kMaxBoxHeight));
+                    s_plan.map_idx[nb] = wi * kMapHCount + hi;
+                    s_plan.row[nb] = row;
+                    row += map_height(hi);
+                    rem -= map_height(hi);
+                    ++nb;
+                }
+                s_plan.n_boxes = nb;
+                s_plan.x = a0 >> 2;
+                s_plan.y0 = by0;
+                s_plan.bytes = (uint32_t)(box_rows * pitch);
+                s_plan.frame0 = g_first + f0 * g_stride;
+                s_plan.frame_step = g_stride;
+                s_plan.src_h = p.src_h;
+                s_plan.n_frames = n_frames;
+                s_plan.fps = fps;
+                s_plan.ring = ring;
+                s_plan.full0 = full0;
+                s_plan.stride = stage_stride;
+                s_plan.frame_bytes = frame_bytes;
+                s_plan.pitch = pitch;
+            }
+            // everybody has read the box: re-arm it for the next item
+            s_box[0] = s_box[2] = 1 << 30;
+            s_box[1] = s_box[3] = -1;
+            s_any = 0;
+        }
+        __syncthreads();  // s_plan visible to the producer lanes
+        // fetch + decode the next item now: nobody waits for thread 0 until the end of this item
+        if (tid == 0)
+            decode(next_item ? (int)gridDim.x + atomicAdd(next_item, 1) : item + (int)gridDim.x,
+                   s_item[par]);
 
         // ---- store geometry ---------------------------------------------------------------------
         // Lanes 4q..4q+2 write words 3q..3q+2 of a 96-byte segment (32 pixels); the four segments
@@ -585,7 +604,7 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
             }
             LoopCtx c;
             c.ring = ring;
-            c.full0 = bar0 + 16 * (1 << slog) - 32;  // the set's empty[] barriers follow its full[]
+            c.full0 = full0;
             c.stride = stage_stride;
             c.frame_bytes = frame_bytes;
             c.pitch = pitch;
@@ -595,16 +614,6 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
             c.plan = &s_plan;
             keep(c.ring);
             keep(c.full0);
-            if (tid == 0) {
-                s_plan.n_frames = n_frames;
-                s_plan.fps = fps;
-                s_plan.ring = c.ring;
-                s_plan.full0 = c.full0;
-                s_plan.stride = c.stride;
-                s_plan.frame_bytes = c.frame_bytes;
-                s_plan.pitch = c.pitch;
-            }
-            __syncthreads();
             // every thread tracks the counter in a register; thread 0 publishes it for the next item
             uint32_t use = s_use[slog - 1];
             if (slog == 3)
@@ -615,6 +624,7 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
                 use = frame_loop<LINEAR, 1>(c, px, use, d, d_step, seg_ok, sel_pack, tid);
             __syncthreads();  // every warp has read s_use and left the ring
             if (tid == 0) s_use[slog - 1] = use;
+            continue;
         } else {
             // bounding box too large for the ring (extreme minification) or too wide / tall for
             // the tensor-map menu: same arithmetic straight from global memory
@@ -648,6 +658,7 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
                 }
             }
         }
+        __syncthreads();  // the next item's descriptor (s_item) is complete and visible
     }
 }
 
@@ -825,9 +836,10 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
     ChunkPlan plan;
     memset(&plan, 0, sizeof(plan));
     const long long tile_groups = n_tiles * p.n_groups;
-    if (max_count >= 128 && tile_groups * 7 >= 2LL * ctas) {
-        static const uint32_t cum[8] = {0, 16384, 32768, 45056, 53248, 59392, 63488, 65536};
-        plan.n_chunks = 7;
+    if (max_count >= 128 && tile_groups * 5 >= 2LL * ctas) {
+        // 5/16, 4/16, 3/16, 5/32, 3/32 of the frames
+        static const uint32_t cum[6] = {0, 20480, 36864, 49152, 59392, 65536};
+        plan.n_chunks = 5;
         memcpy(plan.cum, cum, sizeof(cum));
     } else {
         int k = (int)((3LL * ctas + tile_groups - 1) / tile_groups);
