@@ -70,7 +70,11 @@ __device__ __forceinline__ void project(const Mat3 &H, double x, double y, doubl
     const double X = fma(H.h[0], x, fma(H.h[1], y, H.h[2]));
     const double Y = fma(H.h[3], x, fma(H.h[4], y, H.h[5]));
     const double W = fma(H.h[6], x, fma(H.h[7], y, H.h[8]));
-    const double r = 1.0 / W;
+    // 1/W: hardware seed (2^-23) + one Newton step -> ~2^-45 relative, far inside the 1e-5
+    // contract, at a third of the cost of the IEEE division (W = 0 still gives inf / nan)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(W));
+    r = fma(r, fma(-W, r, 1.0), r);
     u = X * r;
     v = Y * r;
 }
@@ -273,6 +277,158 @@ __global__ void __launch_bounds__(kRows) rows_kernel(const T *__restrict__ in, T
     }
 }
 
+// ---- the pipelined row kernel: whole blocks of 256 rows move with the TMA unit ------------------
+// A block of 256 rows is one contiguous run in global memory (256 * IN * sizeof(T) bytes, always a
+// multiple of 16), so it is fetched with ONE cp.async.bulk into a 3-deep shared-memory ring
+// (completion on an mbarrier) and written back with ONE bulk store out of a 2-deep ring.  The
+// threads only touch shared memory: thread t reads row t (stride IN words -- conflict-free for
+// the odd widths, 64 / 128-bit accesses for the even ones), computes in float64 registers and
+// writes row t of the output block.  Persistent CTAs, blocks strided by gridDim.x.
+namespace bulk {
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void store(void *dst, uint32_t src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// at most one bulk store may still be reading shared memory
+__device__ __forceinline__ void store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// make the threads' shared-memory writes visible to the async proxy (the bulk store)
+__device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// row t of a block: W words at stride W, widest access the row alignment allows
+template <typename T, int W> __device__ __forceinline__ void read_row(const T *base, int t, T (&v)[W])
+{
+    const T *r = base + t * W;
+    if constexpr (sizeof(T) == 4 && W % 4 == 0) {
+#pragma unroll
+        for (int k = 0; k < W; k += 4) {
+            const float4 q = *reinterpret_cast<const float4 *>(r + k);
+            v[k] = q.x; v[k + 1] = q.y; v[k + 2] = q.z; v[k + 3] = q.w;
+        }
+    } else if constexpr (W % 2 == 0 && sizeof(T) == 4) {
+#pragma unroll
+        for (int k = 0; k < W; k += 2) {
+            const float2 q = *reinterpret_cast<const float2 *>(r + k);
+            v[k] = q.x; v[k + 1] = q.y;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < W; ++k) v[k] = r[k];
+    }
+}
+template <typename T, int W> __device__ __forceinline__ void write_row(T *base, int t, const T (&v)[W])
+{
+    T *r = base + t * W;
+    if constexpr (sizeof(T) == 4 && W % 4 == 0) {
+#pragma unroll
+        for (int k = 0; k < W; k += 4)
+            *reinterpret_cast<float4 *>(r + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+    } else if constexpr (W % 2 == 0 && sizeof(T) == 4) {
+#pragma unroll
+        for (int k = 0; k < W; k += 2) *reinterpret_cast<float2 *>(r + k) = make_float2(v[k], v[k + 1]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < W; ++k) r[k] = v[k];
+    }
+}
+}  // namespace bulk
+
+constexpr int kInStages = 3, kOutStages = 2;
+
+template <typename T, typename F>
+__global__ void __launch_bounds__(kRows) rows_bulk_kernel(const T *__restrict__ in, T *__restrict__ out,
+                                                          long long n_blocks, const __grid_constant__ F f)
+{
+    constexpr int IN = F::IN, OUT = F::OUT;
+    constexpr uint32_t in_bytes = kRows * IN * sizeof(T), out_bytes = kRows * OUT * sizeof(T);
+    __shared__ __align__(128) T s_in[kInStages][kRows * IN];
+    __shared__ __align__(128) T s_out[kOutStages][kRows * OUT];
+    __shared__ __align__(8) uint64_t s_bar[kInStages];
+    const int tid = threadIdx.x;
+    const uint32_t bar0 = bulk::smem_u32(s_bar);
+    if (tid == 0) {
+        for (int i = 0; i < kInStages; ++i) bulk::mbar_init(bar0 + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const long long first = blockIdx.x, step = gridDim.x;
+    if (tid == 0)
+        for (int j = 0; j < kInStages - 1; ++j) {
+            const long long b = first + j * step;
+            if (b < n_blocks) {
+                bulk::mbar_expect_tx(bar0 + 8 * j, in_bytes);
+                bulk::load(bulk::smem_u32(s_in[j]), in + b * (kRows * IN), in_bytes, bar0 + 8 * j);
+            }
+        }
+    int slot = 0, oslot = 0;
+    uint32_t phase = 0;
+    for (long long b = first; b < n_blocks; b += step) {
+        if (tid == 0) {
+            // the slot consumed in the previous iteration is free: refill it two blocks ahead
+            const long long nb = b + (kInStages - 1) * step;
+            const int ns = slot == 0 ? kInStages - 1 : slot - 1;
+            if (nb < n_blocks) {
+                bulk::mbar_expect_tx(bar0 + 8 * ns, in_bytes);
+                bulk::load(bulk::smem_u32(s_in[ns]), in + nb * (kRows * IN), in_bytes, bar0 + 8 * ns);
+            }
+            bulk::store_wait_read1();  // the store issued two iterations ago has left s_out[oslot]
+        }
+        bulk::mbar_wait(bar0 + 8 * slot, phase);
+        T vin[IN];
+        bulk::read_row<T, IN>(s_in[slot], tid, vin);
+        __syncthreads();  // s_in[slot] is consumed; s_out[oslot] is free (thread 0 waited above)
+        double a[IN], r[OUT];
+#pragma unroll
+        for (int k = 0; k < IN; ++k) a[k] = (double)vin[k];
+        f.template operator()<T>(a, r);
+        T vout[OUT];
+#pragma unroll
+        for (int k = 0; k < OUT; ++k) vout[k] = (T)r[k];
+        bulk::write_row<T, OUT>(s_out[oslot], tid, vout);
+        bulk::fence_async();
+        __syncthreads();
+        if (tid == 0) bulk::store(out + b * (kRows * OUT), bulk::smem_u32(s_out[oslot]), out_bytes);
+        oslot ^= 1;
+        if (++slot == kInStages) {
+            slot = 0;
+            phase ^= 1;
+        }
+    }
+    if (tid == 0) bulk::store_wait_all();
+}
+
 template <typename F>
 int launch_rows(const void *in, void *out, int64_t n, int dtype, const F &f, cudaStream_t stream,
                 const char *name)
@@ -282,17 +438,35 @@ int launch_rows(const void *in, void *out, int64_t n, int dtype, const F &f, cud
     if (n < 0) BEVK_FAIL(BEVK_E_ARG, "%s: n must be >= 0", name);
     if (n == 0) return BEVK_OK;  // empty input: no launch
     if (!in || !out) BEVK_FAIL(BEVK_E_ARG, "%s: null buffer", name);
-    const long long n_blocks = (n + kRows - 1) / kRows;
-    // 8 resident blocks of 256 threads per SM; a whole number of waves when the batch is large
-    const long long max_grid = (long long)bevk_sm_count() * 8;
-    const int grid = (int)(n_blocks < max_grid ? n_blocks : max_grid);
-    if (dtype == BEVK_F32)
-        rows_kernel<float, F><<<grid, kRows, 0, stream>>>((const float *)in, (float *)out, n, f);
-    else if (dtype == BEVK_F64)
-        rows_kernel<double, F><<<grid, kRows, 0, stream>>>((const double *)in, (double *)out, n, f);
-    else
+    if (dtype != BEVK_F32 && dtype != BEVK_F64)
         BEVK_FAIL(BEVK_E_ARG, "%s: dtype must be BEVK_F32 or BEVK_F64, got %d", name, dtype);
-    BEVK_CUDA(cudaGetLastError());
+    const size_t es = dtype == BEVK_F32 ? 4 : 8;
+    // whole 256-row blocks go through the bulk-copy pipeline when the buffers are 16-byte aligned
+    // (float32 only: the float64 rings would not fit 4 CTAs per SM); the rest -- the tail rows, or
+    // everything for unaligned buffers -- goes through the element-wise staging kernel
+    long long bulk_blocks = 0;
+    if (dtype == BEVK_F32 && ((uintptr_t)in % 16) == 0 && ((uintptr_t)out % 16) == 0) bulk_blocks = n / kRows;
+    if (bulk_blocks > 0) {
+        const long long max_grid = (long long)bevk_sm_count() * 4;
+        const int grid = (int)(bulk_blocks < max_grid ? bulk_blocks : max_grid);
+        rows_bulk_kernel<float, F><<<grid, kRows, 0, stream>>>((const float *)in, (float *)out, bulk_blocks, f);
+        BEVK_CUDA(cudaGetLastError());
+    }
+    const long long done = bulk_blocks * kRows;
+    if (done < n) {
+        const long long rest = n - done;
+        const char *in2 = (const char *)in + (size_t)done * F::IN * es;
+        char *out2 = (char *)out + (size_t)done * F::OUT * es;
+        const long long n_blocks = (rest + kRows - 1) / kRows;
+        // 8 resident blocks of 256 threads per SM; a whole number of waves when the batch is large
+        const long long max_grid = (long long)bevk_sm_count() * 8;
+        const int grid = (int)(n_blocks < max_grid ? n_blocks : max_grid);
+        if (dtype == BEVK_F32)
+            rows_kernel<float, F><<<grid, kRows, 0, stream>>>((const float *)in2, (float *)out2, rest, f);
+        else
+            rows_kernel<double, F><<<grid, kRows, 0, stream>>>((const double *)in2, (double *)out2, rest, f);
+        BEVK_CUDA(cudaGetLastError());
+    }
     return BEVK_OK;
 }
 

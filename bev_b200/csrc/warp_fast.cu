@@ -841,6 +841,17 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
         static const uint32_t cum[6] = {0, 20480, 36864, 49152, 59392, 65536};
         plan.n_chunks = 5;
         memcpy(plan.cum, cum, sizeof(cum));
+        if (const char *e = getenv("BEVK_FAST_CHUNKS")) {  // tuning aid: "a,b,c,..." in 1/64ths
+            int k = 0, acc = 0;
+            plan.cum[0] = 0;
+            for (const char *q = e; *q && k < kMaxChunks;) {
+                acc += atoi(q);
+                plan.cum[++k] = (uint32_t)acc * 1024u;
+                while (*q && *q != ',') ++q;
+                if (*q == ',') ++q;
+            }
+            if (acc == 64) plan.n_chunks = k;
+        }
     } else {
         int k = (int)((3LL * ctas + tile_groups - 1) / tile_groups);
         k = k < 1 ? 1 : k;
