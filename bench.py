@@ -246,6 +246,7 @@ def ours(args, wl):
     # ---- gather of BEV outputs to rank 0 (reported separately from the warp scaling)
     gather = None
     if world > 1:
+        sharding.gather_to_rank0(out[:2])  # connection set-up is not part of the measurement
         torch.cuda.synchronize()
         dist.barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

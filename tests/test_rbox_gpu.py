@@ -139,3 +139,24 @@ def test_large_angles_and_horizon_conditioning():
     y_h = -Hc[2, 2] / Hc[2, 1]  # image row where w = 0
     pts = np.stack([np.linspace(100, 1800, 512), y_h + np.geomspace(0.5, 300, 512)], 1).astype(np.float32)
     check_box(rt.pts_world_bev(cu(pts), Hc), ro.pts_world_bev(pts, Hc))
+
+
+def test_unaligned_views_and_all_row_widths():
+    """A sliced tensor starts 20 bytes into its storage: the 16-byte aligned bulk-copy pipeline
+    must hand it to the element-wise staging kernel.  Also runs every row width (1, 2, 3, 4, 5, 8
+    words in or out) through blocks + tail."""
+    b = boxes(3000, 11)
+    whole = cu(b)
+    Hi = np.linalg.inv(util.h_canon())
+    check_box(rt.xywhr_to_img_corners(whole[1:], Hi, "bev"), ro.xywhr_to_img_corners(b[1:], Hi, "bev"))
+    check_box(rt.xywhr2xyvec(whole, "world"), ro.xywhr2xyvec(b, "world"))
+    check_box(rt.yaw2v(whole[:, 4].contiguous(), "bev"), ro.yaw2v(b[:, 4], "bev"))
+    assert util.rel_err(rt.yaw2mat(whole[:, 4].contiguous(), "world").cpu().numpy(),
+                        ro.yaw2mat(b[:, 4], "world")) <= TOL
+    v = b[:, :2] - 512.0
+    assert util.yaw_err(rt.v2yaw(cu(v), "bev").cpu().numpy(), ro.v2yaw(v, "bev")) <= TOL
+    pts3 = np.concatenate([b[:, :2], np.ones((len(b), 1), np.float32)], 1)
+    check_box(rt.pts_world_bev(cu(pts3), Hi), ro.pts_world_bev(pts3, Hi))
+    check_box(rt.pts_world_bev(cu(b[:, :2]), Hi), ro.pts_world_bev(b[:, :2], Hi))
+    xy8 = ro.xywhr2xyxy(b, "bev").astype(np.float32)
+    check_box(rt.xy82xyvec(cu(xy8)), ro.xy82xyvec(xy8))
