@@ -546,16 +546,17 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
                 s_plan.frame_bytes = frame_bytes;
                 s_plan.pitch = pitch;
             }
-            // everybody has read the box: re-arm it for the next item
+        }
+        __syncthreads();  // s_plan visible to the producer lanes; every thread has read s_box
+        if (tid == 0) {
+            // re-arm the box for the next item (its first atomics come after this item's last
+            // barrier), then fetch + decode the next item: nobody waits for thread 0 until then
             s_box[0] = s_box[2] = 1 << 30;
             s_box[1] = s_box[3] = -1;
             s_any = 0;
-        }
-        __syncthreads();  // s_plan visible to the producer lanes
-        // fetch + decode the next item now: nobody waits for thread 0 until the end of this item
-        if (tid == 0)
             decode(next_item ? (int)gridDim.x + atomicAdd(next_item, 1) : item + (int)gridDim.x,
                    s_item[par]);
+        }
 
         // ---- store geometry ---------------------------------------------------------------------
         // Lanes 4q..4q+2 write words 3q..3q+2 of a 96-byte segment (32 pixels); the four segments
