@@ -134,6 +134,7 @@ struct BevkWarpParams {
 // kernels-side entry points implemented in the .cu files
 int bevk_launch_warp_generic(const BevkWarpParams &p, int channels, int dtype, int linear,
                              cudaStream_t stream);
-// returns 1 if it launched, 0 if the shape does not qualify for the staged path, <0 on error
-int bevk_launch_warp_fast(const BevkWarpParams &p, int channels, int dtype, int linear,
+// returns 1 if it launched, 0 if the shape does not qualify for the staged path (or, unless
+// `force`, is too small a batch to amortise its per-tile set-up), <0 on error
+int bevk_launch_warp_fast(const BevkWarpParams &p, int channels, int dtype, int linear, int force,
                           cudaStream_t stream);

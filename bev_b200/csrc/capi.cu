@@ -234,7 +234,7 @@ int run_warp_device(const void *src, void *dst, const WarpArgs &a,
         }
         int launched = 0;
         if (g_warp_path != 1) {
-            launched = bevk_launch_warp_fast(p, a.channels, a.dtype, a.linear, stream);
+            launched = bevk_launch_warp_fast(p, a.channels, a.dtype, a.linear, g_warp_path == 2, stream);
             if (launched < 0) return launched;
             if (!launched && g_warp_path == 2)
                 BEVK_FAIL(BEVK_E_ARG, "warp: shape does not qualify for the staged fast path");

@@ -792,7 +792,7 @@ void launch(int grid, int smem, cudaStream_t stream, const BevkWarpParams &p, co
 
 }  // namespace
 
-int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, int linear,
+int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, int linear, int force,
                           cudaStream_t stream)
 {
     // qualification: uint8 x 3, zero border, rows the tensor maps / word stores can address,
@@ -820,6 +820,10 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
         n_src_frames = n_src_frames > last + 1 ? n_src_frames : last + 1;
         max_count = max_count > p.g[i].count ? max_count : p.g[i].count;
     }
+    // The staged kernel pays an FP64 set-up per (tile, chunk); with fewer than kMinFrames frames
+    // per homography the direct-gather kernel is faster (measured: 27 vs 39 us for one 1080p frame)
+    constexpr int kMinFrames = 4;
+    if (!force && max_count < kMinFrames) return 0;
     const long long rows = (long long)n_src_frames * p.src_h;
     if (rows > 0x7fffffffLL) return 0;  // TMA coordinates are int32
     WarpFastMaps maps;

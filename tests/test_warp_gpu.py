@@ -13,12 +13,24 @@ from tests import util
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-PATHS = ["generic", "auto"]
+# "fast" forces the staged TMA kernel wherever the shape qualifies (uint8 x 3, zero border), also
+# for the tiny batches that "auto" hands to the direct-gather kernel; other shapes run as "auto".
+PATHS = ["generic", "auto", "fast"]
+_path = {"name": "auto"}
 
 
 def gpu_warp(src_np, H, dsize, flags=1, bv=0, **kw):
     t = torch.from_numpy(np.ascontiguousarray(src_np)).to(DEV)
-    out = homo.warp_perspective(t, H, dsize, flags=flags, borderValue=bv, **kw)
+    try:
+        out = homo.warp_perspective(t, H, dsize, flags=flags, borderValue=bv, **kw)
+    except _native.NativeError as e:
+        if _path["name"] != "fast" or "does not qualify" not in str(e):
+            raise
+        _native.set_warp_path("auto")
+        try:
+            out = homo.warp_perspective(t, H, dsize, flags=flags, borderValue=bv, **kw)
+        finally:
+            _native.set_warp_path("fast")
     assert out.device.type == "cuda" and out.dtype == t.dtype
     return out.cpu().numpy()
 
@@ -26,8 +38,10 @@ def gpu_warp(src_np, H, dsize, flags=1, bv=0, **kw):
 @pytest.fixture(params=PATHS)
 def path(request):
     _native.set_warp_path(request.param)
+    _path["name"] = request.param
     yield request.param
     _native.set_warp_path("auto")
+    _path["name"] = "auto"
 
 
 def test_native_library_is_the_one_running():
@@ -200,3 +214,31 @@ def test_calibration_object_wrappers():
     assert util.sha256(bev[0].cpu().numpy()) == case["sha256"]
     img = homo.warp_bev_to_img(bev, c, b)
     assert tuple(img.shape) == (2, 1080, 1920, 3)
+
+
+@pytest.mark.parametrize("flags", [0, 1])
+def test_staged_kernel_box_shapes(flags):
+    """Shapes that push the staged kernel through every staging mode: one tensor box, several
+    boxes per frame (tall source boxes), boxes too wide / large for the ring (direct global loads
+    inside the same kernel), partial tiles, and frame counts that do not fill the ring stages."""
+    _native.set_warp_path("fast")
+    try:
+        rng = np.random.default_rng(5)
+        frames = np.stack([util.seeded_frame(300 + i, 540, 960, 3, "uint8") for i in range(7)])
+        quad = np.array([[0, 0], [959, 0], [959, 539], [0, 539]], np.float64)
+        cases = [
+            ((256, 256), 0.0),    # ~3.7x / 2.1x minification: wide boxes, ~17 rows
+            ((40, 36), 0.0),      # extreme minification: boxes exceed the menu -> global loads
+            ((130, 520), 30.0),   # tall thin output, vertical magnification, partial tiles
+            ((1000, 12), 10.0),   # wide flat output: strong vertical minification -> many rows
+        ]
+        for (dw, dh), jitter in cases:
+            d = np.array([[0, 0], [dw - 1, 0], [dw - 1, dh - 1], [0, dh - 1]], np.float64)
+            H = homo.homo_from_pts(quad + rng.normal(size=(4, 2)) * jitter, d)
+            dw4 = (dw + 3) // 4 * 4
+            out = gpu_warp(frames, H, (dw4, dh), flags)
+            for i in (0, 3, 6):
+                ref = wo.warp_perspective(frames[i], H, (dw4, dh), flags)
+                assert util.bits_equal(out[i], ref), ((dw, dh), flags, i)
+    finally:
+        _native.set_warp_path("auto")
