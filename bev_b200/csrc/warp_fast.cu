@@ -42,34 +42,61 @@
 
 namespace {
 
-constexpr int kTileW = 128, kTileH = 8, kThreads = 256, kWarps = kThreads / 32;
-// Tensor-map menu: one map per box shape.  Widths 64..512 B in steps of 64 and 640..1024 B in steps
-// of 128; heights 1..8, 10..16 in steps of 2, 20..32 in steps of 4.  A tile's bounding box is
-// fetched with one box whenever it has at most 32 rows (taller ones take up to kMaxBoxes).
-constexpr int kMapWCount = 12, kMapHCount = 16, kMaxBoxWidth = 1024, kMaxBoxHeight = 32;
+constexpr int kThreads = 256, kWarps = kThreads / 32;
+// Tile shapes.  A CTA always owns 1024 dst pixels, 4 per thread; SEGS = 32-pixel segments per tile
+// row: 4 -> 128x8 (warp w owns tile row w), 2 -> 64x16 (rows 2w, 2w+1), 1 -> 32x32 (rows 4w..4w+3).
+// Narrower tiles bound the width of the source box where the map minifies horizontally.
+__host__ __device__ constexpr int tile_w(int segs) { return 32 * segs; }
+__host__ __device__ constexpr int tile_h(int segs) { return kWarps * (4 / segs); }
+// Tensor-map menu: one map per box shape.
+//   narrow boxes: 12 widths (64..512 B in steps of 64, 640..1024 B in steps of 128) x 16 heights
+//                 (1..8, 10..16 in steps of 2, 20..32 in steps of 4), uint32 elements;
+//   wide boxes  :  4 widths (1280..2048 B in steps of 256) x 8 heights (4..32 in steps of 4),
+//                 uint64 elements (a box row holds at most 256 elements).
+// A tile's bounding box is fetched with one box whenever it has at most 32 rows (taller ones take
+// up to kMaxBoxes).
+constexpr int kNarrowW = 12, kNarrowH = 16, kWideW = 4, kWideH = 8;
+constexpr int kMapCount = kNarrowW * kNarrowH + kWideW * kWideH;
+constexpr int kMaxBoxWidth = 2048, kMaxBoxHeight = 32;
 constexpr int kMaxBoxes = 3;
 constexpr int kMaxStageFrames = 4;              // frames that share one ring stage / mbarrier phase
 constexpr int kBarBytes = 256;                  // 28 mbarriers: ring depths 2, 4 and 8
 constexpr int kPrefetchAhead = 2;               // depth-2 rings: L2 prefetch runs this many stages ahead
 constexpr int kTailSlack = 64;                  // window words may run a few bytes past a stage
 
-__host__ __device__ constexpr int map_width(int wi) { return wi < 8 ? 64 * (wi + 1) : 512 + 128 * (wi - 7); }
+__host__ __device__ constexpr int map_width(int wi)
+{
+    return wi < 8 ? 64 * (wi + 1) : (wi < 12 ? 512 + 128 * (wi - 7) : 1024 + 256 * (wi - 11));
+}
+__host__ __device__ constexpr bool map_is_wide(int wi) { return wi >= kNarrowW; }
+// heights of the narrow menu; the wide menu has 4 * (hi + 1)
 __host__ __device__ constexpr int map_height(int hi)
 {
     return hi < 8 ? hi + 1 : (hi < 12 ? 10 + 2 * (hi - 8) : 20 + 4 * (hi - 12));
 }
 // smallest menu entry that covers `bytes` / `rows`
-__device__ __forceinline__ int map_width_index(int bytes)
+__host__ __device__ __forceinline__ int map_width_index(int bytes)
 {
-    return bytes <= 512 ? (bytes + 63) / 64 - 1 : 7 + (bytes - 512 + 127) / 128;
+    return bytes <= 512 ? (bytes + 63) / 64 - 1
+                        : (bytes <= 1024 ? 7 + (bytes - 512 + 127) / 128 : 11 + (bytes - 1024 + 255) / 256);
 }
-__device__ __forceinline__ int map_height_index(int rows)
+__host__ __device__ __forceinline__ int map_height_index(int rows)
 {
     return rows <= 8 ? rows - 1 : (rows <= 16 ? 8 + (rows - 9) / 2 : 12 + (rows - 17) / 4);
 }
+// box height the menu offers for `rows` (<= kMaxBoxHeight) at width index wi, and its map index
+__host__ __device__ __forceinline__ int box_height(int wi, int rows)
+{
+    return map_is_wide(wi) ? (rows + 3) / 4 * 4 : map_height(map_height_index(rows));
+}
+__host__ __device__ __forceinline__ int box_map_index(int wi, int rows)
+{
+    return map_is_wide(wi) ? kNarrowW * kNarrowH + (wi - kNarrowW) * kWideH + (rows + 3) / 4 - 1
+                           : wi * kNarrowH + map_height_index(rows);
+}
 
 struct WarpFastMaps {
-    CUtensorMap m[kMapWCount * kMapHCount];
+    CUtensorMap m[kMapCount];
 };
 
 // Frame chunks of one launch.  Chunk k of a group with `count` frames covers frames
@@ -161,7 +188,7 @@ __device__ __forceinline__ void window(int s, int frac, int n, int &first, int &
 // What the elected producer thread needs to fetch one frame's bounding box.
 struct BoxPlan {
     int n_boxes;
-    int x;                  // first column, in uint32 elements (TMA wants 16-byte aligned box rows)
+    int x;                  // first column, in elements of the map (TMA wants 16-byte aligned box rows)
     int y0;                 // first source row of the box
     uint32_t bytes;         // sum of the box sizes (the mbarrier's transaction count per frame)
     int frame0, frame_step; // source frame of the item's frame i = frame0 + i * frame_step
@@ -280,11 +307,11 @@ __device__ __forceinline__ void feed(const LoopCtx &c, int done, uint32_t use, i
 
 // The frame loop of a staged item.  Ring depth 2^SLOG stages of c.fps frames each.  Returns the
 // advanced stage counter.
-template <bool LINEAR, int SLOG>
+template <bool LINEAR, int SLOG, int SEGS>
 __device__ __forceinline__ uint32_t frame_loop(const LoopCtx &c, const Pix (&px)[4], uint32_t use,
                                                uint8_t *d, const uint32_t d_step,
-                                               const bool (&seg_ok)[4], const uint32_t sel_pack,
-                                               const int tid)
+                                               const uint32_t row_bytes, const bool (&seg_ok)[4],
+                                               const uint32_t sel_pack, const int tid)
 {
     constexpr uint32_t smask = (1u << SLOG) - 1u;
     // Stages in flight besides the one being consumed: half the ring.  The other half is slack
@@ -351,7 +378,8 @@ __device__ __forceinline__ uint32_t frame_loop(const LoopCtx &c, const Pix (&px)
             for (int k = 0; k < 4; ++k) {
                 const uint32_t word = prmt(P[k], __shfl_down_sync(0xffffffffu, P[k], 1), sel_pack);
                 if (seg_ok[k])
-                    st_stream(reinterpret_cast<uint32_t *>(d + 96 * k), word);
+                    st_stream(reinterpret_cast<uint32_t *>(d + 96 * (k % SEGS) + (k / SEGS) * row_bytes),
+                              word);
             }
         }
         ++use;
@@ -359,8 +387,9 @@ __device__ __forceinline__ uint32_t frame_loop(const LoopCtx &c, const Pix (&px)
     return use;
 }
 
-// MINB = CTAs per SM the register allocation is bounded for (4 -> 64 registers, 3 -> 80).
-template <bool LINEAR, int MINB>
+// MINB = CTAs per SM the register allocation is bounded for (4 -> 64 registers, 3 -> 80);
+// SEGS = tile shape (see tile_w / tile_h).
+template <bool LINEAR, int MINB, int SEGS>
 __global__ void __launch_bounds__(kThreads, MINB)
 warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
                       const __grid_constant__ WarpFastMaps maps,
@@ -440,7 +469,9 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
         const int gi = s_item[par].gi, tile_x = s_item[par].tile_x, tile_y = s_item[par].tile_y;
         const int f0 = s_item[par].f0, n_frames = s_item[par].n_frames;
         const int g_first = s_item[par].first, g_stride = s_item[par].stride;
-        const int x0 = tile_x * kTileW, y = tile_y * kTileH + warp;
+        constexpr int kRowsPerWarp = 4 / SEGS;
+        const int x0 = tile_x * tile_w(SEGS), y0 = tile_y * tile_h(SEGS) + warp * kRowsPerWarp;
+        const uint32_t row_bytes = (uint32_t)p.dst_w * 3u;
         par ^= 1;
 
         // ---- 1. set-up ------------------------------------------------------------------------
@@ -448,7 +479,7 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
         int bx0 = 1 << 30, bx1 = -1, by0 = 1 << 30, by1 = -1;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int x = x0 + lane + 32 * k;
+            const int x = x0 + lane + 32 * (k % SEGS), y = y0 + k / SEGS;
             const bool in_dst = (x < p.dst_w) && (y < p.dst_h);
             int X, Y;
             const int xc = min(x, p.dst_w - 1);
@@ -507,7 +538,7 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
         int box_rows = 0;
         if (staged)
             for (int rem = nrows; rem > 0;) {
-                const int h = map_height(map_height_index(min(rem, kMaxBoxHeight)));
+                const int h = box_height(wi, min(rem, kMaxBoxHeight));
                 box_rows += h;
                 rem -= h;
             }
@@ -524,15 +555,15 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
             if (staged) {
                 int rem = nrows, row = 0, nb = 0;
                 while (rem > 0) {
-                    const int hi = map_height_index(min(rem, kMaxBoxHeight));
-                    s_plan.map_idx[nb] = wi * kMapHCount + hi;
+                    const int r = min(rem, kMaxBoxHeight);
+                    s_plan.map_idx[nb] = box_map_index(wi, r);
                     s_plan.row[nb] = row;
-                    row += map_height(hi);
-                    rem -= map_height(hi);
+                    row += box_height(wi, r);
+                    rem -= box_height(wi, r);
                     ++nb;
                 }
                 s_plan.n_boxes = nb;
-                s_plan.x = a0 >> 2;
+                s_plan.x = map_is_wide(wi) ? a0 >> 3 : a0 >> 2;  // in elements of the map
                 s_plan.y0 = by0;
                 s_plan.bytes = (uint32_t)(box_rows * pitch);
                 s_plan.frame0 = g_first + f0 * g_stride;
@@ -567,13 +598,14 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
         bool seg_ok[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int valid_px = min(32, p.dst_w - (x0 + 32 * k));  // multiple of 4 (dst_w % 4 == 0)
-            seg_ok[k] = (y < p.dst_h) && lane_st && (4 * q < valid_px);
+            // pixels left in this 32-pixel segment: a multiple of 4 (dst_w % 4 == 0)
+            const int valid_px = min(32, p.dst_w - (x0 + 32 * (k % SEGS)));
+            seg_ok[k] = (y0 + k / SEGS < p.dst_h) && lane_st && (4 * q < valid_px);
         }
         uint32_t d_step = (uint32_t)g_stride * (uint32_t)p.dst_frame_elems;  // < 2^32 (host check)
         keep(d_step);
         uint8_t *d = dst + (long long)(g_first + f0 * g_stride) * p.dst_frame_elems +
-                     ((long long)y * p.dst_w + x0) * 3 + (3 * q + r4) * 4;
+                     ((long long)y0 * p.dst_w + x0) * 3 + (3 * q + r4) * 4;
 
         if (!any) {
             // whole tile maps outside the source: constant border (0) for every frame
@@ -581,7 +613,8 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
             for (int i = 0; i < n_frames; ++i, d += d_step)
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    if (seg_ok[k]) st_stream(reinterpret_cast<uint32_t *>(d + 96 * k), 0u);
+                    if (seg_ok[k])
+                        st_stream(reinterpret_cast<uint32_t *>(d + 96 * (k % SEGS) + (k / SEGS) * row_bytes), 0u);
         } else if (staged) {
             Pix px[4];
 #pragma unroll
@@ -618,11 +651,11 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
             // every thread tracks the counter in a register; thread 0 publishes it for the next item
             uint32_t use = s_use[slog - 1];
             if (slog == 3)
-                use = frame_loop<LINEAR, 3>(c, px, use, d, d_step, seg_ok, sel_pack, tid);
+                use = frame_loop<LINEAR, 3, SEGS>(c, px, use, d, d_step, row_bytes, seg_ok, sel_pack, tid);
             else if (slog == 2)
-                use = frame_loop<LINEAR, 2>(c, px, use, d, d_step, seg_ok, sel_pack, tid);
+                use = frame_loop<LINEAR, 2, SEGS>(c, px, use, d, d_step, row_bytes, seg_ok, sel_pack, tid);
             else
-                use = frame_loop<LINEAR, 1>(c, px, use, d, d_step, seg_ok, sel_pack, tid);
+                use = frame_loop<LINEAR, 1, SEGS>(c, px, use, d, d_step, row_bytes, seg_ok, sel_pack, tid);
             __syncthreads();  // every warp has read s_use and left the ring
             if (tid == 0) s_use[slog - 1] = use;
             continue;
@@ -655,7 +688,8 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const uint32_t word = prmt(P[k], __shfl_down_sync(0xffffffffu, P[k], 1), sel_pack);
-                    if (seg_ok[k]) st_stream(reinterpret_cast<uint32_t *>(d + 96 * k), word);
+                    if (seg_ok[k])
+                        st_stream(reinterpret_cast<uint32_t *>(d + 96 * (k % SEGS) + (k / SEGS) * row_bytes), word);
                 }
             }
         }
@@ -711,15 +745,18 @@ int get_maps(const void *base, int row_bytes, long long rows, WarpFastMaps &out)
     }
     const cuuint64_t gstride[1] = {(cuuint64_t)row_bytes};
     const cuuint32_t estride[2] = {1, 1};
-    for (int wi = 0; wi < kMapWCount; ++wi)
-        for (int hi = 0; hi < kMapHCount; ++hi) {
-            // uint32 elements: up to 256 per box row = 1024 bytes; every box row starts 16-byte
-            // aligned in global memory, which the TMA unit requires (a start on another byte
-            // raises an illegal-instruction fault -- tried for a 2-byte shifted second copy)
-            const int es = 4;
-            const cuuint64_t gdim[2] = {(cuuint64_t)(row_bytes / es), (cuuint64_t)rows};
-            const cuuint32_t box[2] = {(cuuint32_t)(map_width(wi) / es), (cuuint32_t)map_height(hi)};
-            CUresult r = g_encode(&victim->maps.m[wi * kMapHCount + hi], CU_TENSOR_MAP_DATA_TYPE_UINT32,
+    // every box row starts 16-byte aligned in global memory, which the TMA unit requires (a
+    // start on another byte raises an illegal-instruction fault -- tried for a 2-byte shifted
+    // second copy); 4-byte elements give boxes up to 1024 B wide, 8-byte elements up to 2048 B
+    for (int wi = 0; wi < kNarrowW + kWideW; ++wi) {
+        const bool wide = map_is_wide(wi);
+        const int es = wide ? 8 : 4;
+        const cuuint64_t gdim[2] = {(cuuint64_t)(row_bytes / es), (cuuint64_t)rows};
+        for (int hi = 0; hi < (wide ? kWideH : kNarrowH); ++hi) {
+            const int h = wide ? 4 * (hi + 1) : map_height(hi);
+            const cuuint32_t box[2] = {(cuuint32_t)(map_width(wi) / es), (cuuint32_t)h};
+            CUresult r = g_encode(&victim->maps.m[box_map_index(wi, h)],
+                                  wide ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32,
                                   2, const_cast<void *>(base), gdim, gstride, box, estride,
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -730,6 +767,7 @@ int get_maps(const void *base, int row_bytes, long long rows, WarpFastMaps &out)
                           (int)r, box[0] * es, box[1]);
             }
         }
+    }
     victim->base = base;
     victim->row_bytes = row_bytes;
     victim->rows = rows;
@@ -743,28 +781,19 @@ struct KernelConfig {
     int ctas_per_sm = 0;
     int ring_bytes = 0;
 };
-KernelConfig g_cfg[2][2];  // [linear][MINB - 3]
+constexpr int kMinCtas = 3;  // 80 registers per thread; the 64-register / 4-CTA build spills
+KernelConfig g_cfg[2][3];    // [linear][tile shape: SEGS 4, 2, 1]
+inline int segs_index(int segs) { return segs == 4 ? 0 : (segs == 2 ? 1 : 2); }
 
-// BEVK_FAST_CTAS=3|4 picks the register / occupancy variant (tuning aid); default below.
-int fast_min_ctas()
+template <bool LINEAR, int SEGS> int configure(KernelConfig &cfg)
 {
-    static int v = 0;
-    if (!v) {
-        const char *e = getenv("BEVK_FAST_CTAS");
-        v = (e && (e[0] == '3' || e[0] == '4')) ? e[0] - '0' : 3;
-    }
-    return v;
-}
-
-template <bool LINEAR, int MINB> int configure(KernelConfig &cfg)
-{
-    auto kern = warp_fast_u8c3_kernel<LINEAR, MINB>;
+    auto kern = warp_fast_u8c3_kernel<LINEAR, kMinCtas, SEGS>;
     // how many CTAs the register file allows, then split the shared memory evenly between them
     BEVK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1024));
     int by_regs = 0;
     BEVK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&by_regs, kern, kThreads, 16 * 1024));
     if (by_regs < 1) BEVK_FAIL(BEVK_E_CUDA, "staged warp kernel does not fit an SM");
-    by_regs = by_regs > MINB ? MINB : by_regs;
+    by_regs = by_regs > kMinCtas ? kMinCtas : by_regs;
     int dev = 0, smem_sm = 0;
     BEVK_CUDA(cudaGetDevice(&dev));
     BEVK_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
@@ -782,12 +811,137 @@ template <bool LINEAR, int MINB> int configure(KernelConfig &cfg)
     return BEVK_OK;
 }
 
-template <bool LINEAR, int MINB>
+template <bool LINEAR> int configure_segs(int segs, KernelConfig &cfg)
+{
+    return segs == 4 ? configure<LINEAR, 4>(cfg) : (segs == 2 ? configure<LINEAR, 2>(cfg) : configure<LINEAR, 1>(cfg));
+}
+
+template <bool LINEAR, int SEGS>
 void launch(int grid, int smem, cudaStream_t stream, const BevkWarpParams &p, const WarpFastMaps &maps,
             const ChunkPlan &plan, int tiles_x, int tiles_y, int items, int ring_bytes, int *counter)
 {
-    warp_fast_u8c3_kernel<LINEAR, MINB><<<grid, kThreads, smem, stream>>>(
+    warp_fast_u8c3_kernel<LINEAR, kMinCtas, SEGS><<<grid, kThreads, smem, stream>>>(
         p, maps, plan, tiles_x, tiles_y, items, ring_bytes, counter);
+}
+
+// ---- host side: which tile shape stages --------------------------------------------------------
+// Fraction of the (sampled) tiles of one shape whose source box cannot be staged: wider than the
+// widest tensor box, taller than kMaxBoxes boxes, or larger than half the ring.  The box of a tile
+// is spanned by its four corner pixels (a projective map is monotone along lines as long as w
+// keeps its sign); tiles where w changes sign are left out of the estimate (the kernel copes).
+double unstaged_fraction(const BevkWarpParams &p, int linear, int segs, int ring_bytes)
+{
+    const int tw = tile_w(segs), th = tile_h(segs);
+    const int tiles_x = (p.dst_w + tw - 1) / tw, tiles_y = (p.dst_h + th - 1) / th;
+    // up to 16 x 32 evenly spaced tiles, first and last row / column included
+    const int nsx = tiles_x < 16 ? tiles_x : 16, nsy = tiles_y < 32 ? tiles_y : 32;
+    const double scale = linear ? 32.0 : 1.0;
+    long long active = 0, bad = 0;
+    for (int gi = 0; gi < p.n_groups; ++gi) {
+        const double *M = p.g[gi].M;
+        for (int iy = 0; iy < nsy; ++iy)
+            for (int ix = 0; ix < nsx; ++ix) {
+                const int ty = nsy > 1 ? (int)((long long)iy * (tiles_y - 1) / (nsy - 1)) : 0;
+                const int tx = nsx > 1 ? (int)((long long)ix * (tiles_x - 1) / (nsx - 1)) : 0;
+                const int x0 = tx * tw, y0 = ty * th;
+                const int x1 = (x0 + tw < p.dst_w ? x0 + tw : p.dst_w) - 1;
+                const int y1 = (y0 + th < p.dst_h ? y0 + th : p.dst_h) - 1;
+                const int cx[4] = {x0, x1, x0, x1}, cy[4] = {y0, y0, y1, y1};
+                int lo_x = 1 << 30, hi_x = -(1 << 30), lo_y = 1 << 30, hi_y = -(1 << 30), pos = 0, neg = 0;
+                for (int c = 0; c < 4; ++c) {
+                    const double w = M[6] * cx[c] + M[7] * cy[c] + M[8];
+                    pos += w > 0;
+                    neg += w < 0;
+                    int X, Y;
+                    bevk_map_pixel(M, cx[c], cy[c], p.bw0, scale, X, Y);
+                    const int sx = bevk_sat16(linear ? (X >> 5) : X), sy = bevk_sat16(linear ? (Y >> 5) : Y);
+                    lo_x = sx < lo_x ? sx : lo_x;
+                    hi_x = sx > hi_x ? sx : hi_x;
+                    lo_y = sy < lo_y ? sy : lo_y;
+                    hi_y = sy > hi_y ? sy : hi_y;
+                }
+                hi_x += linear;
+                hi_y += linear;
+                if (hi_x < 0 || hi_y < 0 || lo_x >= p.src_w || lo_y >= p.src_h) continue;  // border only
+                if (pos != 4 && neg != 4) continue;  // horizon inside the tile: corners say nothing
+                ++active;
+                lo_x = lo_x < 0 ? 0 : lo_x;
+                lo_y = lo_y < 0 ? 0 : lo_y;
+                hi_x = hi_x > p.src_w - 1 ? p.src_w - 1 : hi_x;
+                hi_y = hi_y > p.src_h - 1 ? p.src_h - 1 : hi_y;
+                const int a0 = (3 * lo_x) & ~15;
+                const int need_w = ((3 * (hi_x + 1) + 15) & ~15) - a0 + 16;  // one chunk of margin
+                const int rows = hi_y - lo_y + 1 + 1;
+                const int pitch = need_w <= kMaxBoxWidth ? map_width(map_width_index(need_w)) : need_w;
+                if (need_w > kMaxBoxWidth || rows > kMaxBoxes * kMaxBoxHeight ||
+                    2LL * pitch * (rows + 3) > ring_bytes)
+                    ++bad;
+            }
+    }
+    return active ? (double)bad / (double)active : 0.0;
+}
+
+struct ModeKey {
+    double M[BEVK_MAX_GROUPS][9];
+    int n_groups, src_h, src_w, dst_h, dst_w, linear;
+};
+struct ModeEntry {
+    ModeKey key;
+    int segs;  // 4, 2, 1, or 0: leave it to the direct-gather kernel
+    unsigned long long stamp = 0;
+    bool valid = false;
+};
+constexpr int kModeCacheSize = 8;
+ModeEntry g_mode_cache[kModeCacheSize];
+unsigned long long g_mode_stamp = 0;
+
+// Largest tile shape whose boxes all stage; 0 if even the best shape leaves more than
+// kMaxUnstaged of the tiles to the in-kernel fallback (strong minification: the boxes are mostly
+// untouched pixels, the direct-gather kernel moves less data).
+int pick_tile_shape(const BevkWarpParams &p, int linear, int ring_bytes, bool force)
+{
+    // nearest reads one tap per pixel, so its in-kernel fallback costs little: keep wide tiles
+    constexpr double kMaxUnstaged = 0.05;
+    const double kNegligible = linear ? 0.002 : 0.05;
+    ModeKey key;
+    memset(&key, 0, sizeof(key));
+    for (int i = 0; i < p.n_groups; ++i) memcpy(key.M[i], p.g[i].M, sizeof(key.M[i]));
+    key.n_groups = p.n_groups;
+    key.src_h = p.src_h;
+    key.src_w = p.src_w;
+    key.dst_h = p.dst_h;
+    key.dst_w = p.dst_w;
+    key.linear = linear;
+    std::lock_guard<std::mutex> lock(g_map_mutex);
+    ModeEntry *victim = &g_mode_cache[0];  // an empty entry (stamp 0), else the least recently used
+    for (int i = 0; i < kModeCacheSize; ++i) {
+        ModeEntry &e = g_mode_cache[i];
+        if (e.valid && memcmp(&e.key, &key, sizeof(key)) == 0) {
+            e.stamp = ++g_mode_stamp;
+            return (e.segs == 0 && force) ? 1 : e.segs;
+        }
+        if (e.stamp < victim->stamp) victim = &e;
+    }
+    // the widest shape that stages (nearly) everything; else the shape that stages most
+    int best = 0;
+    double best_frac = 2.0;
+    static const int shapes[3] = {4, 2, 1};
+    const char *env = getenv("BEVK_FAST_SEGS");  // tuning aid: force a tile shape
+    for (int si = 0; si < 3; ++si) {
+        if (env && atoi(env) != shapes[si]) continue;
+        const double f = unstaged_fraction(p, linear, shapes[si], ring_bytes);
+        if (f < best_frac - 1e-9) {
+            best_frac = f;
+            best = shapes[si];
+        }
+        if (f <= kNegligible) break;
+    }
+    const int segs = best_frac <= kMaxUnstaged ? best : 0;
+    victim->key = key;
+    victim->segs = segs;
+    victim->stamp = ++g_mode_stamp;
+    victim->valid = true;
+    return (segs == 0 && force) ? (best ? best : 1) : segs;
 }
 
 }  // namespace
@@ -802,14 +956,6 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
     if (p_in.src_w < 2 || p_in.src_h < 2) return 0;
     if ((p_in.src_w * 3) % 16 != 0 || (p_in.dst_w % 4) != 0) return 0;
     if (((uintptr_t)p_in.src % 16) != 0 || ((uintptr_t)p_in.dst % 4) != 0) return 0;
-
-    const int minb = fast_min_ctas();
-    KernelConfig &cfg = g_cfg[linear ? 1 : 0][minb - 3];
-    if (!cfg.ready) {
-        int rc = linear ? (minb == 3 ? configure<true, 3>(cfg) : configure<true, 4>(cfg))
-                        : (minb == 3 ? configure<false, 3>(cfg) : configure<false, 4>(cfg));
-        if (rc) return rc;
-    }
 
     BevkWarpParams p = p_in;
     int n_src_frames = 0, max_count = 0;
@@ -826,37 +972,41 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
     if (!force && max_count < kMinFrames) return 0;
     const long long rows = (long long)n_src_frames * p.src_h;
     if (rows > 0x7fffffffLL) return 0;  // TMA coordinates are int32
+
+    // tile shape: every shape's kernel has the same ring size, so configure the widest first
+    KernelConfig &cfg0 = g_cfg[linear ? 1 : 0][0];
+    if (!cfg0.ready) {
+        int rc = linear ? configure_segs<true>(4, cfg0) : configure_segs<false>(4, cfg0);
+        if (rc) return rc;
+    }
+    const int segs = pick_tile_shape(p, linear, cfg0.ring_bytes, force != 0);
+    if (segs == 0) return 0;
+    KernelConfig &cfg = g_cfg[linear ? 1 : 0][segs_index(segs)];
+    if (!cfg.ready) {
+        int rc = linear ? configure_segs<true>(segs, cfg) : configure_segs<false>(segs, cfg);
+        if (rc) return rc;
+    }
+
     WarpFastMaps maps;
     int rc = get_maps(p.src, p.src_w * 3, rows, maps);
     if (rc) return rc;
 
-    const int tiles_x = (p.dst_w + kTileW - 1) / kTileW, tiles_y = (p.dst_h + kTileH - 1) / kTileH;
+    const int tiles_x = (p.dst_w + tile_w(segs) - 1) / tile_w(segs);
+    const int tiles_y = (p.dst_h + tile_h(segs) - 1) / tile_h(segs);
     const long long n_tiles = (long long)tiles_x * tiles_y;
     const int ctas = bevk_sm_count() * cfg.ctas_per_sm;
 
     // Frame chunks.  Every (tile, chunk) item pays one FP64 set-up, so chunks should be long; the
     // CTAs pull items from a shared counter, so the LAST items should be short.  With enough
-    // frames the chunk lengths therefore decay (1/4, 1/4, 3/16, 1/8, 3/32, 1/16, 1/32 of the
-    // frames); short batches get fewer, equal chunks, just enough for ~3 items per CTA.
+    // frames the chunk lengths therefore decay (5/16, 4/16, 3/16, 5/32, 3/32 of the frames);
+    // short batches get fewer, equal chunks, just enough for ~3 items per CTA.
     ChunkPlan plan;
     memset(&plan, 0, sizeof(plan));
     const long long tile_groups = n_tiles * p.n_groups;
     if (max_count >= 128 && tile_groups * 5 >= 2LL * ctas) {
-        // 5/16, 4/16, 3/16, 5/32, 3/32 of the frames
         static const uint32_t cum[6] = {0, 20480, 36864, 49152, 59392, 65536};
         plan.n_chunks = 5;
         memcpy(plan.cum, cum, sizeof(cum));
-        if (const char *e = getenv("BEVK_FAST_CHUNKS")) {  // tuning aid: "a,b,c,..." in 1/64ths
-            int k = 0, acc = 0;
-            plan.cum[0] = 0;
-            for (const char *q = e; *q && k < kMaxChunks;) {
-                acc += atoi(q);
-                plan.cum[++k] = (uint32_t)acc * 1024u;
-                while (*q && *q != ',') ++q;
-                if (*q == ',') ++q;
-            }
-            if (acc == 64) plan.n_chunks = k;
-        }
     } else {
         int k = (int)((3LL * ctas + tile_groups - 1) / tile_groups);
         k = k < 1 ? 1 : k;
@@ -888,17 +1038,18 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
     if (counter) BEVK_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));
 
     const int smem = cfg.ring_bytes + kBarBytes + kTailSlack;
+#define BEVK_LAUNCH(LIN, SEGS) \
+    launch<LIN, SEGS>(grid, smem, stream, p, maps, plan, tiles_x, tiles_y, (int)items, cfg.ring_bytes, counter)
     if (linear) {
-        if (minb == 3)
-            launch<true, 3>(grid, smem, stream, p, maps, plan, tiles_x, tiles_y, (int)items, cfg.ring_bytes, counter);
-        else
-            launch<true, 4>(grid, smem, stream, p, maps, plan, tiles_x, tiles_y, (int)items, cfg.ring_bytes, counter);
+        if (segs == 4) BEVK_LAUNCH(true, 4);
+        else if (segs == 2) BEVK_LAUNCH(true, 2);
+        else BEVK_LAUNCH(true, 1);
     } else {
-        if (minb == 3)
-            launch<false, 3>(grid, smem, stream, p, maps, plan, tiles_x, tiles_y, (int)items, cfg.ring_bytes, counter);
-        else
-            launch<false, 4>(grid, smem, stream, p, maps, plan, tiles_x, tiles_y, (int)items, cfg.ring_bytes, counter);
+        if (segs == 4) BEVK_LAUNCH(false, 4);
+        else if (segs == 2) BEVK_LAUNCH(false, 2);
+        else BEVK_LAUNCH(false, 1);
     }
+#undef BEVK_LAUNCH
     BEVK_CUDA(cudaGetLastError());
     return 1;
 }

@@ -72,5 +72,48 @@ def main():
         torch.cuda.empty_cache()
 
 
+
+
+def cfg4(n_frames=1000, steps=3):
+    """BASELINE configs[3] on one GPU: 8 BrnoCompSpeed-shaped cameras x n_frames 1080p frames, one
+    homography and one BEV size per camera (tests/golden/cfg4_cams.json)."""
+    import json
+    cams = json.load(open(os.path.join(ROOT, "tests", "golden", "cfg4_cams.json")))
+    peak, _ = bench.measured_peak()
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(1234)
+    frames = torch.randint(0, 256, (n_frames, 1080, 1920, 3), dtype=torch.uint8, device=dev, generator=g)
+    tot_ms, tot_px, tot_bytes = 0.0, 0, 0
+    for c in cams:
+        H = np.array(c["H_bev_img"])
+        dsize = (int(c["bspec"]["u_size"]), int(c["bspec"]["v_size"]))
+        out = torch.empty((n_frames, dsize[1], dsize[0], 3), dtype=torch.uint8, device=dev)
+        T, _, _ = _native.warp_touched_pixels((1920, 1080), dsize, H, 1)
+        algo = (T + dsize[0] * dsize[1]) * 3 * n_frames
+        homo.warp_perspective(frames, H, dsize, dst=out)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            homo.warp_perspective(frames, H, dsize, dst=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        print("cfg4 cam %s bev %dx%d: %.3f ms %.0f Mpix/s frac %.3f" % (
+            c.get("id", "?"), dsize[0], dsize[1], ms, n_frames * dsize[0] * dsize[1] / ms / 1e3,
+            algo / (ms * 1e-3) / 1e9 / peak), flush=True)
+        tot_ms += ms
+        tot_px += n_frames * dsize[0] * dsize[1]
+        tot_bytes += algo
+        del out
+    print("cfg4 total: %.3f ms %.0f Mpix/s frac %.3f" % (tot_ms, tot_px / tot_ms / 1e3,
+                                                         tot_bytes / (tot_ms * 1e-3) / 1e9 / peak))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "cfg4":
+        if len(sys.argv) > 3:
+            _native.set_warp_path(sys.argv[3])
+        cfg4(int(sys.argv[2]) if len(sys.argv) > 2 else 1000)
+    else:
+        main()
