@@ -34,6 +34,7 @@
 // concurrently and near-/far-field tiles mix) plus the output, i.e. the algorithmic bytes of
 // SURVEY.md 8d.
 #include "bevk_common.cuh"
+#include "warp_u8c3.cuh"
 
 #include <cuda.h>  // CUtensorMap + enums only; the encoder is fetched through the runtime
 #include <mutex>
@@ -164,26 +165,8 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr)
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
-{
-    return __byte_perm(a, b, sel);
-}
-__device__ __forceinline__ void st_stream(uint32_t *p, uint32_t v)
-{
-    asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 // Stops the compiler from re-deriving a loop-invariant value inside the frame loop.
 __device__ __forceinline__ void keep(uint32_t &v) { asm volatile("" : "+r"(v)); }
-
-// 2-tap window along one axis: first index (clamped into the image) and the weight each of the
-// two window positions receives.  Taps outside [0, n) contribute nothing (border value 0).
-__device__ __forceinline__ void window(int s, int frac, int n, int &first, int &w0, int &w1)
-{
-    first = min(max(s, 0), n - 2);
-    const int t0 = 32 - frac, t1 = frac;  // weights of taps s and s+1
-    w0 = (first == s ? t0 : 0) + (first == s + 1 ? t1 : 0);
-    w1 = (first + 1 == s ? t0 : 0) + (first + 1 == s + 1 ? t1 : 0);
-}
 
 // What the elected producer thread needs to fetch one frame's bounding box.
 struct BoxPlan {
@@ -207,37 +190,6 @@ struct ItemDesc {
     int f0, n_frames;         // frames [f0, f0 + n_frames) of the group's run
     int first, stride;        // the run: frame index = first + f * stride
 };
-
-// Frame-invariant description of one dst pixel.
-struct Pix {
-    uint32_t addr;   // byte offset (4-aligned) inside a stage of the first window word, row 0
-    uint32_t sh;     // 8 * (window start & 3): funnel-shift amount that byte-aligns the window
-    uint32_t w03;    // bilinear: column weights as bytes 0 and 3 (dp4a with [B0 B1 B2 B3] -> ch. 0)
-                     // nearest : 0x00ffffff when the tap is inside the image, else 0
-    uint32_t w16;    // column weights as 16-bit halves (dp2a lo/hi with [B1 B4 B2 B5] -> ch. 1, 2)
-    uint32_t b0, b1; // row weights * 64
-};
-
-// One pixel out of its staged window: cv2's fixed-point bilinear, result [c0, c1, c2, 0].
-// f0 / g0 = window bytes 0..3 of row 0 / 1, f1 / g1 = window bytes 4.. (already byte-aligned).
-__device__ __forceinline__ uint32_t lerp_aligned(const Pix &q, uint32_t f0, uint32_t f1, uint32_t g0,
-                                                 uint32_t g1)
-{
-    // F = [B0 B1 B2 B3], G = [B1 B4 B2 B5]
-    const uint32_t fg = prmt(f0, f1, 0x5241u), gg = prmt(g0, g1, 0x5241u);
-    // horizontal pass: h[row][channel] = a0 * tap0 + a1 * tap1
-    const uint32_t h00 = __dp4a(f0, q.w03, 0u);
-    const uint32_t h01 = __dp2a_lo(q.w16, fg, 0u);
-    const uint32_t h02 = __dp2a_hi(q.w16, fg, 0u);
-    const uint32_t h10 = __dp4a(g0, q.w03, 0u);
-    const uint32_t h11 = __dp2a_lo(q.w16, gg, 0u);
-    const uint32_t h12 = __dp2a_hi(q.w16, gg, 0u);
-    // vertical pass, scaled by 64: byte 2 of t is (sum w*p + 2^14) >> 15
-    const uint32_t t0 = q.b1 * h10 + (q.b0 * h00 + 32768u);
-    const uint32_t t1 = q.b1 * h11 + (q.b0 * h01 + 32768u);
-    const uint32_t t2 = q.b1 * h12 + (q.b0 * h02 + 32768u);
-    return prmt(prmt(t0, t1, 0x4462u), t2, 0x7610u);
-}
 
 // The consumers' loop state (kept small so that the frame loop fits 64 registers); the elected
 // producer lane reads what it needs from the BoxPlan in shared memory.
@@ -660,8 +612,33 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
             if (tid == 0) s_use[slog - 1] = use;
             continue;
         } else {
-            // bounding box too large for the ring (extreme minification) or too wide / tall for
-            // the tensor-map menu: same arithmetic straight from global memory
+            // bounding box too large for the ring (strong minification) or too wide / tall for the
+            // tensor-map menu: the same arithmetic on aligned 32-bit loads straight from global
+            // memory (L1-cached, read-only path).  Frames are 16-byte aligned (src is, and a frame
+            // is a multiple of 16 bytes), so the window words are addressed like the staged ones.
+            Pix px[4];
+            uint32_t off2[4];  // third window word; clamped into the frame where it is not needed
+            const uint32_t last_word = (uint32_t)p.src_frame_elems - 4u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const bool act = (wc0[k] | wc1[k]) != 0;
+                const uint32_t A = act ? (uint32_t)rs[k] * (uint32_t)src_row_bytes + 3u * (uint32_t)cs[k] : 0u;
+                px[k].addr = A & ~3u;
+                px[k].sh = 8 * (A & 3);
+                if (LINEAR) {
+                    px[k].w03 = wc0[k] | (wc1[k] << 24);
+                    px[k].w16 = wc0[k] | (wc1[k] << 16);
+                    px[k].b0 = wr0[k] * 64;
+                    px[k].b1 = wr1[k] * 64;
+                    // row 1 of the window is read at +src_row_bytes: clamp so that also that read
+                    // stays inside the frame (only a window starting at byte 3 needs the word)
+                    off2[k] = min(px[k].addr + 8u, last_word - (uint32_t)src_row_bytes);
+                } else {
+                    px[k].w03 = act ? 0x00ffffffu : 0u;
+                    px[k].w16 = px[k].b0 = px[k].b1 = 0;
+                    off2[k] = min(px[k].addr + 4u, last_word);
+                }
+            }
             const uint8_t *s = src + (long long)(g_first + f0 * g_stride) * p.src_frame_elems;
             const long long s_step = (long long)g_stride * p.src_frame_elems;
 #pragma unroll 1
@@ -669,21 +646,21 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
                 uint32_t P[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint8_t *t = s + (long long)rs[k] * src_row_bytes + 3 * cs[k];
-                    uint32_t pxv = 0;
+                    const uint8_t *ra = s + px[k].addr;
                     if (LINEAR) {
-#pragma unroll
-                        for (int ch = 0; ch < 3; ++ch) {
-                            const int h0 = wc0[k] * __ldg(t + ch) + wc1[k] * __ldg(t + 3 + ch);
-                            const int h1 = wc0[k] * __ldg(t + src_row_bytes + ch) +
-                                           wc1[k] * __ldg(t + src_row_bytes + 3 + ch);
-                            const uint32_t v = (uint32_t)(wr0[k] * h0 + wr1[k] * h1 + 512) >> 10;
-                            pxv |= v << (8 * ch);
-                        }
-                    } else if (wc0[k]) {
-                        pxv = __ldg(t) | (__ldg(t + 1) << 8) | (__ldg(t + 2) << 16);
+                        const uint8_t *rb = ra + src_row_bytes;
+                        const uint32_t r0 = __ldg((const uint32_t *)ra), r1 = __ldg((const uint32_t *)(ra + 4));
+                        const uint32_t r2 = __ldg((const uint32_t *)(s + off2[k]));
+                        const uint32_t s0 = __ldg((const uint32_t *)rb), s1 = __ldg((const uint32_t *)(rb + 4));
+                        const uint32_t s2 = __ldg((const uint32_t *)(s + off2[k] + src_row_bytes));
+                        const uint32_t sh = px[k].sh;
+                        P[k] = lerp_aligned(px[k], __funnelshift_r(r0, r1, sh), __funnelshift_r(r1, r2, sh),
+                                            __funnelshift_r(s0, s1, sh), __funnelshift_r(s1, s2, sh));
+                    } else {
+                        const uint32_t r0 = __ldg((const uint32_t *)ra);
+                        const uint32_t r1 = __ldg((const uint32_t *)(s + off2[k]));
+                        P[k] = __funnelshift_r(r0, r1, px[k].sh) & px[k].w03;
                     }
-                    P[k] = pxv;
                 }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {

@@ -7,6 +7,7 @@
 // Semantics: cv2.warpPerspective 4.13 (reference call sites vis_homo.py:89,91,
 // bev/tool/compo.py:38,46,47), restated in SURVEY.md Appendix A.
 #include "bevk_common.cuh"
+#include "warp_u8c3.cuh"
 
 namespace {
 
@@ -161,6 +162,106 @@ __global__ void __launch_bounds__(256) warp_nearest_kernel(const __grid_constant
     }
 }
 
+// ---- uint8 x 3, zero border: word gathers + the integer arithmetic of the staged kernel ---------
+// The BGR-video case without shared-memory staging: every lane owns one dst pixel, reads the two
+// 6-byte rows of its 2x2 window as aligned 32-bit words through the read-only L1 path (3 words a
+// row instead of 6 byte loads), interpolates with dp4a / dp2a (warp_u8c3.cuh) and the warp packs
+// its 32 pixels into 24 words -- one coalesced 96-byte store per warp and frame.  This is the
+// kernel for strongly minifying maps (BrnoCompSpeed-sized BEVs of 1080p frames), where a tile's
+// source box is mostly untouched pixels and staging it would move more data than the gather.
+template <bool LINEAR>
+__global__ void __launch_bounds__(256) warp_u8c3_direct_kernel(const __grid_constant__ BevkWarpParams p)
+{
+    const int lane = threadIdx.x, x0 = blockIdx.x * 32;
+    const int x = x0 + lane, y = blockIdx.y * 8 + threadIdx.y;
+    if (y >= p.dst_h) return;  // a warp is one dst row segment: uniform exit, shuffles stay legal
+    int gi;
+    const BevkWarpGroup &g = find_group(p, blockIdx.z, gi);
+    const int c_local = blockIdx.z - g.chunk0;
+    const int f0 = c_local * p.frames_per_chunk;
+    const int f1 = min(f0 + p.frames_per_chunk, g.count);
+
+    int X, Y;
+    bevk_map_pixel(g.M, min(x, p.dst_w - 1), y, p.bw0, LINEAR ? 32.0 : 1.0, X, Y);
+    int cs, rs, wc0, wc1, wr0, wr1;
+    if (LINEAR) {
+        window(bevk_sat16(X >> 5), X & 31, p.src_w, cs, wc0, wc1);
+        window(bevk_sat16(Y >> 5), Y & 31, p.src_h, rs, wr0, wr1);
+    } else {
+        const int sx = bevk_sat16(X), sy = bevk_sat16(Y);
+        const bool in = sx >= 0 && sx < p.src_w && sy >= 0 && sy < p.src_h;
+        cs = min(max(sx, 0), p.src_w - 1);
+        rs = min(max(sy, 0), p.src_h - 1);
+        wc0 = wr0 = in ? 1 : 0;
+        wc1 = wr1 = 0;
+    }
+    const bool act = (wc0 | wc1) != 0 && (wr0 | wr1) != 0;
+    const uint32_t row_bytes = (uint32_t)p.src_w * 3u;
+    const uint32_t A = act ? (uint32_t)rs * row_bytes + 3u * (uint32_t)cs : 0u;
+    const uint32_t last_word = (uint32_t)p.src_frame_elems - 4u;
+    Pix q;
+    q.addr = A & ~3u;
+    q.sh = 8 * (A & 3);
+    uint32_t off2;  // third (nearest: second) window word, clamped into the frame where unused
+    if (LINEAR) {
+        q.w03 = act ? (wc0 | (wc1 << 24)) : 0;
+        q.w16 = act ? (wc0 | (wc1 << 16)) : 0;
+        q.b0 = wr0 * 64;
+        q.b1 = wr1 * 64;
+        off2 = min(q.addr + 8u, last_word - row_bytes);
+    } else {
+        q.w03 = act ? 0x00ffffffu : 0u;
+        q.w16 = q.b0 = q.b1 = 0;
+        off2 = min(q.addr + 4u, last_word);
+    }
+    // lanes 4j..4j+2 write words 3j..3j+2 of the warp's 96-byte segment
+    const int j = lane >> 2, r4 = lane & 3;
+    const uint32_t sel_pack = r4 == 0 ? 0x4210u : (r4 == 1 ? 0x5421u : 0x6542u);
+    const bool st_ok = r4 < 3 && 4 * j < min(32, p.dst_w - x0);  // dst_w % 4 == 0
+    const uint8_t *src = (const uint8_t *)p.src;
+    uint8_t *dst = (uint8_t *)p.dst + ((long long)y * p.dst_w + x0) * 3 + (3 * j + r4) * 4;
+
+#pragma unroll 2
+    for (int f = f0; f < f1; ++f) {
+        const long long fr = (long long)(g.first + f * g.stride);
+        const uint8_t *s = src + fr * p.src_frame_elems;
+        uint32_t P;
+        if (LINEAR) {
+            const uint8_t *ra = s + q.addr, *rb = ra + row_bytes;
+            const uint32_t r0 = __ldg((const uint32_t *)ra), r1 = __ldg((const uint32_t *)(ra + 4));
+            const uint32_t r2 = __ldg((const uint32_t *)(s + off2));
+            const uint32_t s0 = __ldg((const uint32_t *)rb), s1 = __ldg((const uint32_t *)(rb + 4));
+            const uint32_t s2 = __ldg((const uint32_t *)(s + off2 + row_bytes));
+            P = lerp_aligned(q, __funnelshift_r(r0, r1, q.sh), __funnelshift_r(r1, r2, q.sh),
+                             __funnelshift_r(s0, s1, q.sh), __funnelshift_r(s1, s2, q.sh));
+        } else {
+            const uint32_t r0 = __ldg((const uint32_t *)(s + q.addr));
+            const uint32_t r1 = __ldg((const uint32_t *)(s + off2));
+            P = __funnelshift_r(r0, r1, q.sh) & q.w03;
+        }
+        const uint32_t word = prmt(P, __shfl_down_sync(0xffffffffu, P, 1), sel_pack);
+        if (st_ok) st_stream(reinterpret_cast<uint32_t *>(dst + fr * p.dst_frame_elems), word);
+    }
+}
+
+// returns true if it launched
+bool launch_u8c3_direct(const BevkWarpParams &p, int linear, cudaStream_t stream)
+{
+    if (p.border[0] != 0.f || p.border[1] != 0.f || p.border[2] != 0.f) return false;
+    // rows of a multiple of 4 bytes: both rows of a window then share one word alignment
+    if (p.src_w < 2 || p.src_h < 2 || (p.src_w % 4) != 0 || (p.dst_w % 4) != 0) return false;
+    if (((uintptr_t)p.src % 4) != 0 || ((uintptr_t)p.dst % 4) != 0) return false;
+    if ((p.src_frame_elems % 4) != 0 || (p.dst_frame_elems % 4) != 0) return false;
+    if (p.src_frame_elems > 0xffffffffLL) return false;
+    dim3 block(32, 8, 1);
+    dim3 grid((p.dst_w + 31) / 32, (p.dst_h + 7) / 8, p.total_chunks);
+    if (linear)
+        warp_u8c3_direct_kernel<true><<<grid, block, 0, stream>>>(p);
+    else
+        warp_u8c3_direct_kernel<false><<<grid, block, 0, stream>>>(p);
+    return true;
+}
+
 template <typename T, int C>
 int launch_tc(const BevkWarpParams &p, int linear, cudaStream_t stream)
 {
@@ -191,6 +292,10 @@ int launch_t(const BevkWarpParams &p, int channels, int linear, cudaStream_t str
 int bevk_launch_warp_generic(const BevkWarpParams &p, int channels, int dtype, int linear,
                              cudaStream_t stream)
 {
+    if (dtype == BEVK_U8 && channels == 3 && launch_u8c3_direct(p, linear, stream)) {
+        BEVK_CUDA(cudaGetLastError());
+        return BEVK_OK;
+    }
     switch (dtype) {
     case BEVK_U8: return launch_t<uint8_t>(p, channels, linear, stream);
     case BEVK_F16: return launch_t<__half>(p, channels, linear, stream);
