@@ -8,12 +8,12 @@ projection of points / rotated boxes, behind the reference's own Python surface
 The compute runs in hand-written CUDA kernels for sm_100a in ``libbev_b200.so`` (C ABI in
 include/bev_b200.h).  There is no CPU fallback.
 """
-from . import homo, rbox_torch
+from . import compo, homo, rbox_torch
 from .bev import BEVWorldSpec
 from .calib import Calib
 from .frozen_class import FrozenClass
 
-__all__ = ["homo", "rbox_torch", "BEVWorldSpec", "Calib", "FrozenClass", "install_as_bev"]
+__all__ = ["homo", "rbox_torch", "compo", "BEVWorldSpec", "Calib", "FrozenClass", "install_as_bev"]
 
 
 def install_as_bev():
@@ -24,6 +24,6 @@ def install_as_bev():
     me = sys.modules[__name__]
     sys.modules["bev"] = me
     for name, mod in (("homo", homo), ("rbox_torch", rbox_torch), ("bev", _bev),
-                      ("calib", _calib), ("frozen_class", _fc)):
+                      ("calib", _calib), ("frozen_class", _fc), ("tool.compo", compo)):
         sys.modules["bev." + name] = mod
     return me

@@ -39,6 +39,7 @@ SIGNATURES = {
     "bevk_warp_host_rows": (_c_int, [_c_int, _c_int, _c_int, _c_int, _dp, _c_int, _c_int, _ip]),
     "bevk_warp_set_path": (_c_int, [_c_int]),
     "bevk_warp_touched_pixels": (_c_i64, [_c_int, _c_int, _c_int, _c_int, _dp, _c_int, _ip]),
+    "bevk_composite_u8c3": (_c_int, [_vp, _vp, _vp, _vp, _c_i64, _c_int, _vp]),
     "bevk_pts_project": (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _dp, _vp]),
     "bevk_xywhr2xyxy": (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _dp, _vp]),
     "bevk_xy82xywhr": (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _dp, _vp]),
@@ -294,4 +295,26 @@ def rows_op(name, x, in_cols, out_shape_tail, *extra, H=None, has_H=False):
         args.append(_stream_ptr(x))
         rc = getattr(lib(), name)(*args)
     _check(rc, name)
+    return out
+
+
+def composite_u8c3(bg, fg, fg_mask, bw_mode=False, out=None):
+    """out = uint8(round(fg * mask/255 + bg * (1 - mask/255))) on CUDA uint8 tensors of one shape
+    (..., 3); bit-identical to the reference's numpy float64 blend (bev/tool/compo.py:16-23)."""
+    import torch
+    for name, t in (("bg", bg), ("fg", fg), ("fg_mask", fg_mask)):
+        _require_cuda(t, name)
+        if t.dtype != torch.uint8:
+            raise TypeError("%s must be uint8, got %s" % (name, t.dtype))
+    if not (tuple(bg.shape) == tuple(fg.shape) == tuple(fg_mask.shape)) or bg.shape[-1] != 3:
+        raise ValueError("bg, fg and fg_mask must share one (..., 3) shape; got %s %s %s"
+                         % (tuple(bg.shape), tuple(fg.shape), tuple(fg_mask.shape)))
+    bg, fg, fg_mask = bg.contiguous(), fg.contiguous(), fg_mask.contiguous()
+    if out is None:
+        out = torch.empty_like(bg)
+    n_pixels = bg.numel() // 3
+    with torch.cuda.device(bg.device):
+        rc = lib().bevk_composite_u8c3(_vp(bg.data_ptr()), _vp(fg.data_ptr()), _vp(fg_mask.data_ptr()),
+                                       _vp(out.data_ptr()), n_pixels, int(bool(bw_mode)), _stream_ptr(bg))
+    _check(rc, "bevk_composite_u8c3")
     return out

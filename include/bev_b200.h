@@ -104,6 +104,18 @@ int64_t bevk_warp_touched_pixels(int src_h, int src_w, int dst_h, int dst_w, con
                                  int flags, int *row_range);
 
 /*
+ * Alpha compositing of uint8 BGR frames, the blend behind the three warps of
+ * bev/tool/compo.py:38,46,47 -- replaces composite_reg_img (bev/tool/compo.py:5-24):
+ *     out = uint8(min(round_half_even(fg * (mask / 255) + bg * (1 - mask / 255)), 255))
+ * evaluated like the reference's numpy float64 expression (bit-identical).  bg, fg, fg_mask and
+ * out are device buffers of n_pixels x 3 bytes (any batch of same-sized frames, flattened;
+ * 4-byte aligned).  bw_mode != 0 first turns fg grey the way
+ * cv2.cvtColor(BGR2GRAY) -> GRAY2BGR does (compo.py:13-14).
+ */
+int bevk_composite_u8c3(const void *bg, const void *fg, const void *fg_mask, void *out,
+                        int64_t n_pixels, int bw_mode, void *stream);
+
+/*
  * Homogeneous point projection with divide.  Replaces rbox.pts_world_bev (bev/rbox.py:136-151)
  * and the cv2.perspectiveTransform call sites (bev/visualizer/rbox_vis.py:54,61,74).
  *   pts/out [n][dim], dim 2 (w = 1 implied, 2 columns out) or 3 (homogeneous in, 3 columns out,

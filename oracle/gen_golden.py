@@ -39,7 +39,7 @@ from bev.bev import BEVWorldSpec  # noqa: E402
 from bev.constructor.homo_constr import preset_calib, preset_bspec, load_bspec  # noqa: E402
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-from oracle.synth import seeded_frame  # noqa: E402
+from oracle.synth import seeded_frame, compo_inputs  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
 OUT = os.path.normpath(OUT)
@@ -301,11 +301,49 @@ def gen_warp():
         json.dump({"cv2_version": cv2.__version__, "cases": hashes}, f, indent=1)
 
 
+def compo_camera():
+    """The fixed geometry of the compositing fixture (a KoPER-like camera over a 160x120 BEV)."""
+    K = np.array([[300.0, 0, 120], [0, 300.0, 80], [0, 0, 1]])
+    RT = np.eye(4)
+    RT[:3, :3] = cv2.Rodrigues(np.array([2.2, 0.05, -0.03]))[0]
+    RT[:3, 3] = [0.3, 1.5, 14.0]
+    H_world2bev = np.array([[8.0, 0, 80], [0, -8.0, 100], [0, 0, 1]])
+    Kfix = np.array([[310.0, 0, 118], [0, 305.0, 82], [0, 0, 1]])
+    RTfix = np.eye(4)
+    RTfix[:3, :3] = cv2.Rodrigues(np.array([2.15, 0.02, 0.04]))[0]
+    RTfix[:3, 3] = [-0.2, 1.2, 15.0]
+    H_img2world_fix = np.linalg.inv(ref_homo.homo_from_KRt(Kfix, Rt_homo=RTfix))
+    return K, RT, H_world2bev, H_img2world_fix
+
+
+def gen_compo():
+    """Outputs of the reference's bev/tool/compo.py (composite_reg_img / composite_bev_img)."""
+    import bev.tool.compo as ref_compo
+    out = {}
+    bg, fg, mask = compo_inputs(4242, 161, 241)  # odd sizes: pixel count not a multiple of 4
+    out["reg"] = ref_compo.composite_reg_img(bg, fg, mask)
+    out["reg_bw"] = ref_compo.composite_reg_img(bg, fg, mask, bw_mode=True)
+    K, RT, H_world2bev, H_img2world_fix = compo_camera()
+    bg, fg, mask = compo_inputs(4343, 160, 240)
+    for tag, bw in (("bev", False), ("bev_bw", True)):
+        c, Hcam = ref_compo.composite_bev_img(bg, fg, mask, H_world2bev, H_img2world_fix, K, RT,
+                                              160, 120, bw_mode=bw)
+        out[tag] = c
+        out[tag + "_Hcam"] = Hcam
+    for k, v in (("K", K), ("RT", RT), ("H_world2bev", H_world2bev), ("H_img2world_fix", H_img2world_fix)):
+        out[k] = v
+    np.savez_compressed(os.path.join(OUT, "compo_kat.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "compo":
+        gen_compo()
+        sys.exit(0)
     gen_homo_kat()
     gen_cfg4()
     gen_rbox_kat()
     gen_warp()
+    gen_compo()
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))
