@@ -44,6 +44,8 @@ SIGNATURES = {
     "bevk_xywhr2xyxy": (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _dp, _vp]),
     "bevk_xy82xywhr": (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _dp, _vp]),
     "bevk_rbox_world_bev": (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _dp, _vp]),
+    "bevk_rboxtt_world_bev": (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _dp, _vp]),
+    "bevk_rbox_zt2tt_world": (_c_int, [_vp, _vp, _c_i64, _c_int, _dp, _dp, _vp]),
     "bevk_xywhr2xyvec": (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _vp]),
     "bevk_xy82xyvec": (_c_int, [_vp, _vp, _c_i64, _c_int, _vp]),
     "bevk_v2yaw": (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _vp]),
@@ -317,4 +319,24 @@ def composite_u8c3(bg, fg, fg_mask, bw_mode=False, out=None):
         rc = lib().bevk_composite_u8c3(_vp(bg.data_ptr()), _vp(fg.data_ptr()), _vp(fg_mask.data_ptr()),
                                        _vp(out.data_ptr()), n_pixels, int(bool(bw_mode)), _stream_ptr(bg))
     _check(rc, "bevk_composite_u8c3")
+    return out
+
+
+def rbox_zt2tt_world(x, K, Rt):
+    """(N,7) world boxes with height -> (N,7) ground boxes with a projected height tail."""
+    import torch
+    _require_cuda(x, "input")
+    code = _proj_dtype(x)
+    if x.dim() != 2 or x.shape[1] != 7:
+        raise ValueError("rbox_zt2tt_world expects shape (N, 7), got %s" % (tuple(x.shape),))
+    Kn = np.ascontiguousarray(np.asarray(_to_numpy(K), np.float64)[:3, :3])
+    Rn = np.ascontiguousarray(np.asarray(_to_numpy(Rt), np.float64)[:3, :4])
+    if Kn.shape != (3, 3) or Rn.shape != (3, 4):
+        raise ValueError("K must be 3x3 (or 3x4) and Rt 3x4 (or 4x4)")
+    x2 = x.contiguous()
+    out = torch.empty_like(x2)
+    with torch.cuda.device(x.device):
+        rc = lib().bevk_rbox_zt2tt_world(_vp(x2.data_ptr()), _vp(out.data_ptr()), x2.shape[0], code,
+                                         _dptr(Kn), _dptr(Rn), _stream_ptr(x))
+    _check(rc, "bevk_rbox_zt2tt_world")
     return out

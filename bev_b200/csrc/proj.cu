@@ -158,6 +158,54 @@ struct FnSimilarity {  // rbox_world_bev                                   rbox_
     }
 };
 
+struct FnRboxTT {  // rboxtt_world_bev: similarity of xywhr + the height tail (du, dv)   rbox.py:258-288
+    static constexpr int IN = 7, OUT = 7;
+    FnSimilarity sim;
+    template <typename T> __device__ __forceinline__ void operator()(const double *in, double *out) const
+    {
+        sim.template operator()<T>(in, out);
+        const Mat3 &H = sim.H;  // affine (asserted on the host): tail = H [x+du, y+dv, 1] - H [x, y, 1]
+        const double ex = in[0] + in[5], ey = in[1] + in[6];
+        out[5] = fma(H.h[0], ex, fma(H.h[1], ey, H.h[2])) - out[0];
+        out[6] = fma(H.h[3], ex, fma(H.h[4], ey, H.h[5])) - out[1];
+    }
+};
+
+struct FnZt2tt {  // rbox_zt2tt_world: (x, y, w, h, r, z, t) -> (x', y', w, h, r, du, dv)   rbox.py:228-256
+    static constexpr int IN = 7, OUT = 7;
+    double K[9], R[9], t[3];
+    Mat3 Hwc;  // inv(K [r1 r2 t]): image -> world plane z = 0
+    __device__ __forceinline__ void ground(double x, double y, double z, double &gx, double &gy) const
+    {
+        const double cx = fma(R[0], x, fma(R[1], y, fma(R[2], z, t[0])));
+        const double cy = fma(R[3], x, fma(R[4], y, fma(R[5], z, t[1])));
+        const double cz = fma(R[6], x, fma(R[7], y, fma(R[8], z, t[2])));
+        const double u = fma(K[0], cx, fma(K[1], cy, K[2] * cz));
+        const double v = fma(K[3], cx, fma(K[4], cy, K[5] * cz));
+        const double d = fma(K[6], cx, fma(K[7], cy, K[8] * cz));
+        const double dc = d < 1e-2 ? 1e-2 : d;  // np.clip(uvd[2], a_min=1e-2)
+        const double a = u / dc, b = v / dc, c = d / dc;
+        const double X = fma(Hwc.h[0], a, fma(Hwc.h[1], b, Hwc.h[2] * c));
+        const double Y = fma(Hwc.h[3], a, fma(Hwc.h[4], b, Hwc.h[5] * c));
+        const double W = fma(Hwc.h[6], a, fma(Hwc.h[7], b, Hwc.h[8] * c));
+        gx = X / W;
+        gy = Y / W;
+    }
+    template <typename T> __device__ __forceinline__ void operator()(const double *in, double *out) const
+    {
+        double lx, ly, hx, hy;
+        ground(in[0], in[1], in[5], lx, ly);
+        ground(in[0], in[1], in[5] + in[6], hx, hy);
+        out[0] = lx;
+        out[1] = ly;
+        out[2] = in[2];
+        out[3] = in[3];
+        out[4] = in[4];
+        out[5] = hx - lx;
+        out[6] = hy - ly;
+    }
+};
+
 struct FnPts2 {  // pts_world_bev, (N,2)                                           rbox.py:136-151
     static constexpr int IN = 2, OUT = 2;
     Mat3 H;
@@ -526,23 +574,62 @@ int bevk_xy82xywhr(const void *xy8, void *xywhr, int64_t n, int mode, int dtype,
 }
 
 int bevk_rbox_world_bev(const void *xywhr_in, void *xywhr_out, int64_t n, int src_mode, int dtype,
-                        const double H[9], void *stream)
+                        const double H[9], void *stream);
+
+// shared by bevk_rbox_world_bev / bevk_rboxtt_world_bev: normalise H, check the reference's asserts
+static int make_similarity(const double H[9], int src_mode, const char *name, FnSimilarity &f)
 {
-    if (int rc = check_mode(src_mode, "bevk_rbox_world_bev")) return rc;
-    if (!H) BEVK_FAIL(BEVK_E_ARG, "bevk_rbox_world_bev: H is null");
-    FnSimilarity f;
+    if (int rc = check_mode(src_mode, name)) return rc;
+    if (!H) BEVK_FAIL(BEVK_E_ARG, "%s: H is null", name);
     for (int i = 0; i < 9; ++i) f.H.h[i] = H[i] / H[8];  // rbox_torch.py:139
-    // the reference's two asserts (rbox_torch.py:140,161), checked on the host before any launch
     if (!(fabs(f.H.h[6]) + fabs(f.H.h[7]) < 1e-5))
-        BEVK_FAIL(BEVK_E_AFFINE, "bevk_rbox_world_bev: H is not affine (|H20|+|H21| = %g)",
+        BEVK_FAIL(BEVK_E_AFFINE, "%s: H is not affine (|H20|+|H21| = %g)", name,
                   fabs(f.H.h[6]) + fabs(f.H.h[7]));
     const double s0 = sqrt(f.H.h[0] * f.H.h[0] + f.H.h[1] * f.H.h[1]);
     const double s1 = sqrt(f.H.h[3] * f.H.h[3] + f.H.h[4] * f.H.h[4]);
     if (!(fabs(s0 - s1) < 1e-5))
-        BEVK_FAIL(BEVK_E_AFFINE, "bevk_rbox_world_bev: H is not a similarity (scales %g vs %g)", s0, s1);
+        BEVK_FAIL(BEVK_E_AFFINE, "%s: H is not a similarity (scales %g vs %g)", name, s0, s1);
     f.scale = s0;
     f.src_mode = src_mode;
+    return BEVK_OK;
+}
+
+int bevk_rbox_world_bev(const void *xywhr_in, void *xywhr_out, int64_t n, int src_mode, int dtype,
+                        const double H[9], void *stream)
+{
+    FnSimilarity f;
+    if (int rc = make_similarity(H, src_mode, "bevk_rbox_world_bev", f)) return rc;
     return launch_rows(xywhr_in, xywhr_out, n, dtype, f, (cudaStream_t)stream, "bevk_rbox_world_bev");
+}
+
+int bevk_rboxtt_world_bev(const void *in, void *out, int64_t n, int src_mode, int dtype, const double H[9],
+                          void *stream)
+{
+    FnRboxTT f;
+    if (int rc = make_similarity(H, src_mode, "bevk_rboxtt_world_bev", f.sim)) return rc;
+    return launch_rows(in, out, n, dtype, f, (cudaStream_t)stream, "bevk_rboxtt_world_bev");
+}
+
+int bevk_rbox_zt2tt_world(const void *in, void *out, int64_t n, int dtype, const double K[9],
+                          const double Rt[12], void *stream)
+{
+    if (!K || !Rt) BEVK_FAIL(BEVK_E_ARG, "bevk_rbox_zt2tt_world: K / Rt is null");
+    FnZt2tt f;
+    double Hcw[9];  // homo_from_KRt: K [r1 r2 t]
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) {
+            f.K[3 * i + j] = K[3 * i + j];
+            f.R[3 * i + j] = Rt[4 * i + j];
+        }
+        f.t[i] = Rt[4 * i + 3];
+    }
+    for (int i = 0; i < 3; ++i) {
+        const int cols[3] = {0, 1, 3};
+        for (int j = 0; j < 3; ++j)
+            Hcw[3 * i + j] = K[3 * i] * Rt[cols[j]] + K[3 * i + 1] * Rt[4 + cols[j]] + K[3 * i + 2] * Rt[8 + cols[j]];
+    }
+    if (!bevk_invert3x3(Hcw, f.Hwc.h)) BEVK_FAIL(BEVK_E_ARG, "bevk_rbox_zt2tt_world: K [r1 r2 t] is singular");
+    return launch_rows(in, out, n, dtype, f, (cudaStream_t)stream, "bevk_rbox_zt2tt_world");
 }
 
 int bevk_xywhr2xyvec(const void *xywhr, void *xyvec, int64_t n, int mode, int dtype, void *stream)

@@ -101,3 +101,26 @@ def xywhr_to_img_corners(xywhr, H, mode):
 def img_corners_to_xywhr(xy8, H, mode):
     """Project 4 corners with H, then xy82xywhr, in one pass (the way back of configs[2])."""
     return _native.rows_op("bevk_xy82xywhr", xy8, 8, (5,), _mode(mode), H=H, has_H=True)
+
+
+# ---- 7-dof boxes: ground box + projected height tail (reference bev/rbox.py:228-314, numpy only) ----
+
+def rboxtt_world_bev(rbox_src, H, src):
+    """(N,7) [x,y,w,h,yaw,du,dv] between world and BEV through an affine similarity H
+    (reference rbox.py:258-288; same asserts on H as ``rbox_world_bev``)."""
+    return _native.rows_op("bevk_rboxtt_world_bev", rbox_src, 7, (7,), _mode(src), H=H, has_H=True)
+
+
+def rbox_zt2tt_world(rboxzt, K, Rt):
+    """(N,7) world boxes [x,y,w,h,yaw,z,t] -> [x',y',w,h,yaw,du,dv]: foot and top of the box seen
+    by the camera K [R|t], dropped back onto the ground plane (reference rbox.py:228-256)."""
+    return _native.rbox_zt2tt_world(rboxzt, K, Rt)
+
+
+def rboxzt_world_bev(rbox_src, H, K, Rt, src):
+    """World boxes with height -> BEV boxes with a height tail (reference rbox.py:291-314; like
+    the reference only ``src == "world"`` is provided)."""
+    assert src in _MODES
+    if src != "world":
+        raise NotImplementedError("rboxzt_world_bev only supports converting from world to bev")
+    return rboxtt_world_bev(rbox_zt2tt_world(rbox_src, K, Rt), H, src)

@@ -149,6 +149,23 @@ int bevk_xy82xywhr(const void *xy8, void *xywhr, int64_t n, int mode, int dtype,
 int bevk_rbox_world_bev(const void *xywhr_in, void *xywhr_out, int64_t n, int src_mode, int dtype,
                         const double H[9], void *stream);
 
+/*
+ * 7-dof boxes with a projected height tail (x, y, w, h, yaw, du, dv).  Replaces
+ * rbox.rboxtt_world_bev (bev/rbox.py:258-288): the first five columns go through
+ * bevk_rbox_world_bev, the tail through the linear part of the same (affine) H.
+ */
+int bevk_rboxtt_world_bev(const void *rboxtt_in, void *rboxtt_out, int64_t n, int src_mode, int dtype,
+                          const double H[9], void *stream);
+/*
+ * World boxes with height (x, y, w, h, yaw, z, t) -> ground boxes with a height tail
+ * (x', y', w, h, yaw, du, dv): the box foot (x, y, z) and its top (x, y, z + t) are projected into
+ * the camera K [R|t] (depth clipped at 1e-2) and back onto the ground plane through
+ * inv(K [r1 r2 t]).  Replaces rbox.rbox_zt2tt_world (bev/rbox.py:228-256).
+ * K: HOST 3x3 float64, Rt: HOST 3x4 float64 (row-major [R|t]).
+ */
+int bevk_rbox_zt2tt_world(const void *rboxzt, void *rboxtt, int64_t n, int dtype, const double K[9],
+                          const double Rt[12], void *stream);
+
 /* Heading segments [n][4] = [x, y, x + h*dx, y + h*dy].  rbox_torch.xywhr2xyvec (:101-112). */
 int bevk_xywhr2xyvec(const void *xywhr, void *xyvec, int64_t n, int mode, int dtype, void *stream);
 /* Heading segments from corners.  rbox_torch.xy82xyvec (:114-121). */

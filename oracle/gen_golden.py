@@ -335,15 +335,35 @@ def gen_compo():
     np.savez_compressed(os.path.join(OUT, "compo_kat.npz"), **out)
 
 
+def gen_rbox7():
+    """Outputs of the reference's 7-dof box functions (bev/rbox.py:228-314)."""
+    rng = np.random.default_rng(77)
+    n = 300
+    zt = np.stack([rng.uniform(-20, 20, n), rng.uniform(5, 60, n), rng.uniform(1.5, 2.5, n),
+                   rng.uniform(3, 12, n), rng.uniform(-np.pi, np.pi, n), rng.uniform(0, 0.5, n),
+                   rng.uniform(1.2, 3.5, n)], 1)
+    K, RT, H_world2bev, _ = compo_camera()
+    out = {"zt": zt, "K": K, "Rt": RT, "H": H_world2bev}
+    out["zt2tt"] = ref_rbox.rbox_zt2tt_world(zt.copy(), K, RT)
+    out["tt_bev"] = ref_rbox.rboxtt_world_bev(out["zt2tt"].copy(), H_world2bev, "world")
+    out["tt_back"] = ref_rbox.rboxtt_world_bev(out["tt_bev"].copy(), np.linalg.inv(H_world2bev), "bev")
+    out["zt_bev"] = ref_rbox.rboxzt_world_bev(zt.copy(), H_world2bev, K, RT, "world")
+    np.savez_compressed(os.path.join(OUT, "rbox7_kat.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1 and sys.argv[1] == "compo":
         gen_compo()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "rbox7":
+        gen_rbox7()
         sys.exit(0)
     gen_homo_kat()
     gen_cfg4()
     gen_rbox_kat()
     gen_warp()
     gen_compo()
+    gen_rbox7()
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))

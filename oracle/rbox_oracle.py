@@ -171,3 +171,53 @@ def img_corners_to_xywhr(xy8, H, mode):
     """The way back: project 4 corners with H, then xy82xywhr."""
     c = pts_world_bev(_f64(xy8).reshape(-1, 2), H).reshape(-1, 8)
     return xy82xywhr(c, mode)
+
+
+# --- 7-dof boxes (ground box + height tail), rbox.py:228-314 -------------------------------------
+
+def homo_from_KRt(K, Rt):
+    """bev/homo.py:6-26 (Rt_homo form): K [r1 r2 t]."""
+    return _f64(K)[:, :3].dot(_f64(Rt)[:3][:, [0, 1, 3]])
+
+
+def rbox_zt2tt_world(rboxzt, K, Rt):
+    """rbox.py:228-256."""
+    rboxzt, K, Rt = _f64(rboxzt), _f64(K), _f64(Rt)
+    H_world_cam = np.linalg.inv(homo_from_KRt(K, Rt))
+
+    def ground(xyz):
+        cam = Rt[:3, :3].dot(xyz) + Rt[:3, [3]]
+        uvd = K.dot(cam)
+        uv1 = uvd / np.clip(uvd[2], a_min=1e-2, a_max=None)
+        xy1 = H_world_cam.dot(uv1)
+        return xy1 / xy1[2]
+
+    low = rboxzt[:, [0, 1, 5]].T
+    high = low.copy()
+    high[2] = high[2] + rboxzt[:, 6]
+    xy_low, xy_high = ground(low), ground(high)
+    return np.concatenate([xy_low[:2].T, rboxzt[:, 2:5], (xy_high[:2] - xy_low[:2]).T], axis=1)
+
+
+def rboxtt_world_bev(box, H, src):
+    """rbox.py:258-288."""
+    assert src in _MODES
+    box, H = _f64(box), _f64(H)
+    if len(box) == 0:
+        return box
+    H = H / H[2, 2]
+    assert abs(H[2, 0]) + abs(H[2, 1]) < 1e-5
+    assert box.shape[1] == 7
+    one = np.ones((box.shape[0], 1))
+    start = H.dot(np.concatenate([box[:, :2], one], axis=1).T)
+    end = H.dot(np.concatenate([box[:, :2] + box[:, 5:], one], axis=1).T)
+    dudv = (end - start)[:2].T
+    return np.concatenate([rbox_world_bev(box[:, :5], H, src), dudv], axis=1)
+
+
+def rboxzt_world_bev(box, H, K, Rt, src):
+    """rbox.py:291-314 (world -> bev only, like the reference)."""
+    assert src in _MODES
+    if src != "world":
+        raise NotImplementedError("rboxzt_world_bev only supports converting from world to bev")
+    return rboxtt_world_bev(rbox_zt2tt_world(box, K, Rt), H, src)

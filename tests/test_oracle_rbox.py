@@ -83,3 +83,16 @@ def test_reference_fp32_twin_is_looser_than_oracle():
     # ~1e-6 .. 1e-5 relative from it on plain corners
     e = util.rel_err(K["xywhr2xyxy_t32_bev"], K["xywhr2xyxy_bev"])
     assert 0 < e < 1e-4
+
+
+def test_seven_dof_boxes_match_the_reference():
+    """oracle rbox_zt2tt_world / rboxtt_world_bev / rboxzt_world_bev vs the reference's own
+    outputs (bev/rbox.py:228-314 run in the build container, tests/golden/rbox7_kat.npz)."""
+    K7 = util.load_npz("rbox7_kat.npz")
+    assert np.abs(ro.rbox_zt2tt_world(K7["zt"], K7["K"], K7["Rt"]) - K7["zt2tt"]).max() < 1e-12
+    assert np.abs(ro.rboxtt_world_bev(K7["zt2tt"], K7["H"], "world") - K7["tt_bev"]).max() < 1e-12
+    back = ro.rboxtt_world_bev(K7["tt_bev"], np.linalg.inv(K7["H"]), "bev")
+    assert np.abs(back - K7["tt_back"]).max() < 1e-12
+    assert np.abs(ro.rboxzt_world_bev(K7["zt"], K7["H"], K7["K"], K7["Rt"], "world") - K7["zt_bev"]).max() < 1e-12
+    # the BEV -> world -> BEV round trip of the tail is the identity
+    assert np.abs(back[:, [0, 1, 2, 3, 5, 6]] - K7["zt2tt"][:, [0, 1, 2, 3, 5, 6]]).max() < 1e-9

@@ -160,3 +160,26 @@ def test_unaligned_views_and_all_row_widths():
     check_box(rt.pts_world_bev(cu(b[:, :2]), Hi), ro.pts_world_bev(b[:, :2], Hi))
     xy8 = ro.xywhr2xyxy(b, "bev").astype(np.float32)
     check_box(rt.xy82xyvec(cu(xy8)), ro.xy82xyvec(xy8))
+
+
+def test_seven_dof_boxes():
+    """rbox_zt2tt_world / rboxtt_world_bev / rboxzt_world_bev (reference bev/rbox.py:228-314,
+    numpy only there) against the reference's outputs and the float64 oracle."""
+    K7 = util.load_npz("rbox7_kat.npz")
+    zt = K7["zt"].astype(np.float32)
+    ref_tt = ro.rbox_zt2tt_world(zt, K7["K"], K7["Rt"])
+    tt = rt.rbox_zt2tt_world(cu(zt), K7["K"], K7["Rt"])
+    check_box(tt, ref_tt, yaw_col=4)
+    tt32 = tt.cpu().numpy()
+    check_box(rt.rboxtt_world_bev(tt, K7["H"], "world"), ro.rboxtt_world_bev(tt32, K7["H"], "world"), yaw_col=4)
+    check_box(rt.rboxzt_world_bev(cu(zt), K7["H"], K7["K"], K7["Rt"], "world"),
+              ro.rboxzt_world_bev(zt, K7["H"], K7["K"], K7["Rt"], "world"), yaw_col=4)
+    # float64 tensors reproduce the reference's own numbers
+    out = rt.rboxzt_world_bev(cu(K7["zt"], np.float64), K7["H"], K7["K"], K7["Rt"], "world").cpu().numpy()
+    assert util.rel_err(out[:, [0, 1, 2, 3, 5, 6]], K7["zt_bev"][:, [0, 1, 2, 3, 5, 6]]) < 1e-10
+    assert util.yaw_err(out[:, 4], K7["zt_bev"][:, 4]) < 1e-10
+    with pytest.raises(NotImplementedError):
+        rt.rboxzt_world_bev(cu(zt), K7["H"], K7["K"], K7["Rt"], "bev")
+    with pytest.raises(AssertionError):
+        rt.rboxtt_world_bev(tt, util.h_canon(), "world")  # not affine
+    assert tuple(rt.rboxtt_world_bev(torch.zeros((0, 7), device=DEV), K7["H"], "bev").shape) == (0, 7)
