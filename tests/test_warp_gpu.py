@@ -242,3 +242,22 @@ def test_staged_kernel_box_shapes(flags):
                 assert util.bits_equal(out[i], ref), ((dw, dh), flags, i)
     finally:
         _native.set_warp_path("auto")
+
+
+@pytest.mark.parametrize("flags", [1, 0])
+def test_cfg2_full_batch(flags):
+    """BASELINE configs[1] at full size: 256 x 1080p -> 1024^2 in one call.  Three frames are
+    checked bit for bit against the oracle; the rest through a size-independent property -- the
+    batch contains every frame twice (i and i + 128), so both halves of the output must agree,
+    whatever chunk, tile or ring slot a frame went through."""
+    H = util.h_canon()
+    g = torch.Generator(device=DEV).manual_seed(7)
+    half = torch.randint(0, 256, (128, 1080, 1920, 3), dtype=torch.uint8, device=DEV, generator=g)
+    frames = torch.cat([half, half], 0)
+    del half
+    out = homo.warp_perspective(frames, H, (1024, 1024), flags=flags)
+    assert tuple(out.shape) == (256, 1024, 1024, 3)
+    assert torch.equal(out[:128], out[128:])
+    for i in (0, 77, 255):
+        ref = wo.warp_perspective(frames[i].cpu().numpy(), H, (1024, 1024), flags)
+        assert util.bits_equal(out[i].cpu().numpy(), ref), i
