@@ -258,25 +258,26 @@ __device__ __forceinline__ void feed(const LoopCtx &c, int done, uint32_t use, i
 }
 
 // The frame loop of a staged item.  Ring depth 2^SLOG stages of c.fps frames each.  Returns the
-// advanced stage counter.
-template <bool LINEAR, int SLOG, int SEGS>
-__device__ __forceinline__ uint32_t frame_loop(const LoopCtx &c, const Pix (&px)[4], uint32_t use,
-                                               uint8_t *d, const uint32_t d_step,
+// advanced stage counter.  PX = pixel format policy (warp_u8c3.cuh / warp_f16c3.cuh).
+template <typename PX, bool LINEAR, int SLOG, int SEGS>
+__device__ __forceinline__ uint32_t frame_loop(const LoopCtx &c, const typename PX::Reg (&px)[4],
+                                               uint32_t use, uint8_t *d, const uint32_t d_step,
                                                const uint32_t row_bytes, const bool (&seg_ok)[4],
-                                               const uint32_t sel_pack, const int tid)
+                                               const typename PX::Store st, const int tid)
 {
     constexpr uint32_t smask = (1u << SLOG) - 1u;
     // Stages in flight besides the one being consumed: half the ring.  The other half is slack
     // between the warps -- a slot is refilled S/2 stages after its last use, so the refilling lane
     // practically never waits for a slower warp to release it.
     constexpr int ahead = 1 << (SLOG - 1);
+    constexpr uint32_t kLast = PX::template last_word_offset<LINEAR>();
     const int lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
-        for (int st = 0; st < ahead && st * c.fps < c.n_frames; ++st)
-            produce<SLOG, true>(c.plan, c.maps, st * c.fps, use + st);
+        for (int s = 0; s < ahead && s * c.fps < c.n_frames; ++s)
+            produce<SLOG, true>(c.plan, c.maps, s * c.fps, use + s);
         if (SLOG == 1)
-            for (int st = ahead; st < ahead + kPrefetchAhead && st * c.fps < c.n_frames; ++st)
-                produce<SLOG, false>(c.plan, c.maps, st * c.fps, 0);
+            for (int s = ahead; s < ahead + kPrefetchAhead && s * c.fps < c.n_frames; ++s)
+                produce<SLOG, false>(c.plan, c.maps, s * c.fps, 0);
     }
 
     int done = 0;
@@ -291,48 +292,24 @@ __device__ __forceinline__ uint32_t frame_loop(const LoopCtx &c, const Pix (&px)
 #pragma unroll 1
         for (; nf > 0; --nf, sa += c.frame_bytes, d += d_step) {
             const uint32_t sb = sa + c.pitch;  // row 1
-            uint32_t P[4];
-            if (LINEAR) {
+            typename PX::Out P[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t a = px[k].addr + sa, b = px[k].addr + sb;
-                    const uint32_t r0 = lds32(a), r1 = lds32(a + 4), r2 = lds32(a + 8);
-                    const uint32_t s0 = lds32(b), s1 = lds32(b + 4), s2 = lds32(b + 8);
-                    if (k == 3 && nf == 1) {
-                        // every shared-memory read of this stage is issued: hand the slot back
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(fb + (8u << SLOG));
-                        feed<SLOG>(c, done, use, lane, warp);
-                    }
-                    // byte-align the window of both rows
-                    const uint32_t sh = px[k].sh;
-                    P[k] = lerp_aligned(px[k], __funnelshift_r(r0, r1, sh), __funnelshift_r(r1, r2, sh),
-                                        __funnelshift_r(s0, s1, sh), __funnelshift_r(s1, s2, sh));
-                }
-            } else {
-                uint32_t w[4][2];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    w[k][0] = lds32(px[k].addr + sa);
-                    w[k][1] = lds32(px[k].addr + sa + 4);
-                }
-                if (nf == 1) {
+            for (int k = 0; k < 4; ++k) {
+                uint32_t w[8];
+                const uint32_t a = px[k].addr + sa, b = px[k].addr + sb;
+                PX::template load<LINEAR>(px[k], a, b, a + kLast, b + kLast, w, [](uint32_t ad) { return lds32(ad); });
+                if (k == 3 && nf == 1) {
+                    // every shared-memory read of this stage is issued: hand the slot back
                     __syncwarp();
                     if (lane == 0) mbar_arrive(fb + (8u << SLOG));
                     feed<SLOG>(c, done, use, lane, warp);
                 }
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    P[k] = __funnelshift_r(w[k][0], w[k][1], px[k].sh) & px[k].w03;
+                P[k] = PX::template math<LINEAR>(px[k], w);
             }
-            // pack 4 lanes x 3 bytes into 3 words and store 96-byte segments
+            // pack the lanes' pixels into words and store coalesced row segments
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t word = prmt(P[k], __shfl_down_sync(0xffffffffu, P[k], 1), sel_pack);
-                if (seg_ok[k])
-                    st_stream(reinterpret_cast<uint32_t *>(d + 96 * (k % SEGS) + (k / SEGS) * row_bytes),
-                              word);
-            }
+            for (int k = 0; k < 4; ++k)
+                PX::store(d + PX::kSegBytes * (k % SEGS) + (k / SEGS) * row_bytes, P[k], seg_ok[k], st, lane);
         }
         ++use;
     }
@@ -341,9 +318,9 @@ __device__ __forceinline__ uint32_t frame_loop(const LoopCtx &c, const Pix (&px)
 
 // MINB = CTAs per SM the register allocation is bounded for (4 -> 64 registers, 3 -> 80);
 // SEGS = tile shape (see tile_w / tile_h).
-template <bool LINEAR, int MINB, int SEGS>
+template <typename PX, bool LINEAR, int MINB, int SEGS>
 __global__ void __launch_bounds__(kThreads, MINB)
-warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
+warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
                       const __grid_constant__ WarpFastMaps maps,
                       const __grid_constant__ ChunkPlan plan, const int tiles_x, const int tiles_y,
                       const int total_items, const int ring_bytes, int *const next_item)
@@ -379,7 +356,10 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
     const int n_tiles = tiles_x * tiles_y;
     const uint8_t *src = (const uint8_t *)p.src;
     uint8_t *dst = (uint8_t *)p.dst;
-    const int src_row_bytes = p.src_w * 3;
+    constexpr int kBpp = PX::kBpp;
+    const int src_row_bytes = p.src_w * kBpp;
+    const long long src_frame_bytes = (long long)src_row_bytes * p.src_h;
+    const long long dst_frame_bytes = (long long)p.dst_w * p.dst_h * kBpp;
 
     // Items are (chunk, group, tile) with the chunk index slowest: long chunks first.  The first
     // gridDim.x items are taken by block index, the rest are pulled from *next_item.
@@ -423,7 +403,7 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
         const int g_first = s_item[par].first, g_stride = s_item[par].stride;
         constexpr int kRowsPerWarp = 4 / SEGS;
         const int x0 = tile_x * tile_w(SEGS), y0 = tile_y * tile_h(SEGS) + warp * kRowsPerWarp;
-        const uint32_t row_bytes = (uint32_t)p.dst_w * 3u;
+        const uint32_t row_bytes = (uint32_t)p.dst_w * (uint32_t)kBpp;
         par ^= 1;
 
         // ---- 1. set-up ------------------------------------------------------------------------
@@ -480,8 +460,8 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
         by1 = s_box[3];
 
         // staged geometry: 16-byte aligned first column, box shapes from the tensor-map menu
-        const int a0 = (3 * bx0) & ~15;
-        const int need_w = ((3 * (bx1 + 1) + 15) & ~15) - a0;
+        const int a0 = (kBpp * bx0) & ~15;
+        const int need_w = ((kBpp * (bx1 + 1) + 15) & ~15) - a0;
         const int wi = map_width_index(need_w);
         const int pitch = map_width(wi);
         const int nrows = by1 - by0 + 1;
@@ -542,22 +522,19 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
         }
 
         // ---- store geometry ---------------------------------------------------------------------
-        // Lanes 4q..4q+2 write words 3q..3q+2 of a 96-byte segment (32 pixels); the four segments
-        // of this warp's tile row are 96 bytes apart.
-        const int q = lane >> 2, r4 = lane & 3;
-        const uint32_t sel_pack = r4 == 0 ? 0x4210u : (r4 == 1 ? 0x5421u : 0x6542u);
-        const bool lane_st = r4 < 3;
+        // which words of a 32-pixel row segment this lane writes is the pixel format's business
+        const typename PX::Store st = PX::store_setup(lane);
         bool seg_ok[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             // pixels left in this 32-pixel segment: a multiple of 4 (dst_w % 4 == 0)
             const int valid_px = min(32, p.dst_w - (x0 + 32 * (k % SEGS)));
-            seg_ok[k] = (y0 + k / SEGS < p.dst_h) && lane_st && (4 * q < valid_px);
+            seg_ok[k] = (y0 + k / SEGS < p.dst_h) && PX::lane_stores(lane, valid_px);
         }
-        uint32_t d_step = (uint32_t)g_stride * (uint32_t)p.dst_frame_elems;  // < 2^32 (host check)
+        uint32_t d_step = (uint32_t)g_stride * (uint32_t)dst_frame_bytes;  // < 2^32 (host check)
         keep(d_step);
-        uint8_t *d = dst + (long long)(g_first + f0 * g_stride) * p.dst_frame_elems +
-                     ((long long)y0 * p.dst_w + x0) * 3 + (3 * q + r4) * 4;
+        uint8_t *d = dst + (long long)(g_first + f0 * g_stride) * dst_frame_bytes +
+                     ((long long)y0 * p.dst_w + x0) * kBpp + PX::lane_offset(lane);
 
         if (!any) {
             // whole tile maps outside the source: constant border (0) for every frame
@@ -565,28 +542,16 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
             for (int i = 0; i < n_frames; ++i, d += d_step)
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    if (seg_ok[k])
-                        st_stream(reinterpret_cast<uint32_t *>(d + 96 * (k % SEGS) + (k / SEGS) * row_bytes), 0u);
+                    PX::store_zero(d + PX::kSegBytes * (k % SEGS) + (k / SEGS) * row_bytes, seg_ok[k], lane);
         } else if (staged) {
-            Pix px[4];
+            typename PX::Reg px[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const bool act = (wc0[k] | wc1[k]) != 0;
-                const int A = act ? (rs[k] - by0) * pitch + 3 * cs[k] - a0 : 0;
-                px[k].addr = A & ~3;
-                px[k].sh = 8 * (A & 3);
-                if (LINEAR) {
-                    px[k].w03 = wc0[k] | (wc1[k] << 24);
-                    px[k].w16 = wc0[k] | (wc1[k] << 16);
-                    px[k].b0 = wr0[k] * 64;
-                    px[k].b1 = wr1[k] * 64;
-                } else {
-                    px[k].w03 = act ? 0x00ffffffu : 0u;
-                    px[k].w16 = px[k].b0 = px[k].b1 = 0;
-                }
+                const int A = act ? (rs[k] - by0) * pitch + kBpp * cs[k] - a0 : 0;
+                px[k] = PX::template make<LINEAR>(act, (uint32_t)A, wc0[k], wc1[k], wr0[k], wr1[k]);
                 keep(px[k].addr);
                 keep(px[k].sh);
-                keep(px[k].w03);
             }
             LoopCtx c;
             c.ring = ring;
@@ -603,11 +568,11 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
             // every thread tracks the counter in a register; thread 0 publishes it for the next item
             uint32_t use = s_use[slog - 1];
             if (slog == 3)
-                use = frame_loop<LINEAR, 3, SEGS>(c, px, use, d, d_step, row_bytes, seg_ok, sel_pack, tid);
+                use = frame_loop<PX, LINEAR, 3, SEGS>(c, px, use, d, d_step, row_bytes, seg_ok, st, tid);
             else if (slog == 2)
-                use = frame_loop<LINEAR, 2, SEGS>(c, px, use, d, d_step, row_bytes, seg_ok, sel_pack, tid);
+                use = frame_loop<PX, LINEAR, 2, SEGS>(c, px, use, d, d_step, row_bytes, seg_ok, st, tid);
             else
-                use = frame_loop<LINEAR, 1, SEGS>(c, px, use, d, d_step, row_bytes, seg_ok, sel_pack, tid);
+                use = frame_loop<PX, LINEAR, 1, SEGS>(c, px, use, d, d_step, row_bytes, seg_ok, st, tid);
             __syncthreads();  // every warp has read s_use and left the ring
             if (tid == 0) s_use[slog - 1] = use;
             continue;
@@ -616,58 +581,36 @@ warp_fast_u8c3_kernel(const __grid_constant__ BevkWarpParams p,
             // tensor-map menu: the same arithmetic on aligned 32-bit loads straight from global
             // memory (L1-cached, read-only path).  Frames are 16-byte aligned (src is, and a frame
             // is a multiple of 16 bytes), so the window words are addressed like the staged ones.
-            Pix px[4];
-            uint32_t off2[4];  // third window word; clamped into the frame where it is not needed
-            const uint32_t last_word = (uint32_t)p.src_frame_elems - 4u;
+            constexpr uint32_t kLast = PX::template last_word_offset<LINEAR>();
+            typename PX::Reg px[4];
+            uint32_t last[4];  // last window word; clamped into the frame where it is not needed
+            const uint32_t last_word = (uint32_t)src_frame_bytes - 4u;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const bool act = (wc0[k] | wc1[k]) != 0;
-                const uint32_t A = act ? (uint32_t)rs[k] * (uint32_t)src_row_bytes + 3u * (uint32_t)cs[k] : 0u;
-                px[k].addr = A & ~3u;
-                px[k].sh = 8 * (A & 3);
-                if (LINEAR) {
-                    px[k].w03 = wc0[k] | (wc1[k] << 24);
-                    px[k].w16 = wc0[k] | (wc1[k] << 16);
-                    px[k].b0 = wr0[k] * 64;
-                    px[k].b1 = wr1[k] * 64;
-                    // row 1 of the window is read at +src_row_bytes: clamp so that also that read
-                    // stays inside the frame (only a window starting at byte 3 needs the word)
-                    off2[k] = min(px[k].addr + 8u, last_word - (uint32_t)src_row_bytes);
-                } else {
-                    px[k].w03 = act ? 0x00ffffffu : 0u;
-                    px[k].w16 = px[k].b0 = px[k].b1 = 0;
-                    off2[k] = min(px[k].addr + 4u, last_word);
-                }
+                const uint32_t A = act ? (uint32_t)rs[k] * (uint32_t)src_row_bytes + (uint32_t)kBpp * (uint32_t)cs[k] : 0u;
+                px[k] = PX::template make<LINEAR>(act, A, wc0[k], wc1[k], wr0[k], wr1[k]);
+                // bilinear reads row 1 of the window at +src_row_bytes: clamp so that also that
+                // read stays inside the frame (the alignments that need the word never clamp)
+                last[k] = min(px[k].addr + kLast, last_word - (LINEAR ? (uint32_t)src_row_bytes : 0u));
             }
-            const uint8_t *s = src + (long long)(g_first + f0 * g_stride) * p.src_frame_elems;
-            const long long s_step = (long long)g_stride * p.src_frame_elems;
+            const uint8_t *s = src + (long long)(g_first + f0 * g_stride) * src_frame_bytes;
+            const long long s_step = (long long)g_stride * src_frame_bytes;
 #pragma unroll 1
             for (int i = 0; i < n_frames; ++i, d += d_step, s += s_step) {
-                uint32_t P[4];
+                typename PX::Out P[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint8_t *ra = s + px[k].addr;
-                    if (LINEAR) {
-                        const uint8_t *rb = ra + src_row_bytes;
-                        const uint32_t r0 = __ldg((const uint32_t *)ra), r1 = __ldg((const uint32_t *)(ra + 4));
-                        const uint32_t r2 = __ldg((const uint32_t *)(s + off2[k]));
-                        const uint32_t s0 = __ldg((const uint32_t *)rb), s1 = __ldg((const uint32_t *)(rb + 4));
-                        const uint32_t s2 = __ldg((const uint32_t *)(s + off2[k] + src_row_bytes));
-                        const uint32_t sh = px[k].sh;
-                        P[k] = lerp_aligned(px[k], __funnelshift_r(r0, r1, sh), __funnelshift_r(r1, r2, sh),
-                                            __funnelshift_r(s0, s1, sh), __funnelshift_r(s1, s2, sh));
-                    } else {
-                        const uint32_t r0 = __ldg((const uint32_t *)ra);
-                        const uint32_t r1 = __ldg((const uint32_t *)(s + off2[k]));
-                        P[k] = __funnelshift_r(r0, r1, px[k].sh) & px[k].w03;
-                    }
+                    uint32_t w[8];
+                    // "addresses" are byte offsets inside the frame here
+                    PX::template load<LINEAR>(px[k], px[k].addr, px[k].addr + src_row_bytes, last[k],
+                                              last[k] + src_row_bytes, w,
+                                              [s](uint32_t off) { return __ldg((const uint32_t *)(s + off)); });
+                    P[k] = PX::template math<LINEAR>(px[k], w);
                 }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t word = prmt(P[k], __shfl_down_sync(0xffffffffu, P[k], 1), sel_pack);
-                    if (seg_ok[k])
-                        st_stream(reinterpret_cast<uint32_t *>(d + 96 * (k % SEGS) + (k / SEGS) * row_bytes), word);
-                }
+                for (int k = 0; k < 4; ++k)
+                    PX::store(d + PX::kSegBytes * (k % SEGS) + (k / SEGS) * row_bytes, P[k], seg_ok[k], st, lane);
             }
         }
         __syncthreads();  // the next item's descriptor (s_item) is complete and visible
@@ -764,7 +707,7 @@ inline int segs_index(int segs) { return segs == 4 ? 0 : (segs == 2 ? 1 : 2); }
 
 template <bool LINEAR, int SEGS> int configure(KernelConfig &cfg)
 {
-    auto kern = warp_fast_u8c3_kernel<LINEAR, kMinCtas, SEGS>;
+    auto kern = warp_fast_kernel<PxU8C3, LINEAR, kMinCtas, SEGS>;
     // how many CTAs the register file allows, then split the shared memory evenly between them
     BEVK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1024));
     int by_regs = 0;
@@ -797,7 +740,7 @@ template <bool LINEAR, int SEGS>
 void launch(int grid, int smem, cudaStream_t stream, const BevkWarpParams &p, const WarpFastMaps &maps,
             const ChunkPlan &plan, int tiles_x, int tiles_y, int items, int ring_bytes, int *counter)
 {
-    warp_fast_u8c3_kernel<LINEAR, kMinCtas, SEGS><<<grid, kThreads, smem, stream>>>(
+    warp_fast_kernel<PxU8C3, LINEAR, kMinCtas, SEGS><<<grid, kThreads, smem, stream>>>(
         p, maps, plan, tiles_x, tiles_y, items, ring_bytes, counter);
 }
 

@@ -55,3 +55,90 @@ __device__ __forceinline__ uint32_t lerp_aligned(const Pix &q, uint32_t f0, uint
     return prmt(prmt(t0, t1, 0x4462u), t2, 0x7610u);
 }
 
+
+// ---- the pixel-format policy the staged kernel (warp_fast.cu) is written against ---------------
+// uint8 x 3 (BGR video): 3 bytes per pixel; a 2-tap window row is 6 bytes starting on any byte,
+// i.e. up to 3 aligned words; 32 pixels are 96 bytes = 24 words.
+struct PxU8C3 {
+    static constexpr int kBpp = 3;         // bytes per pixel
+    static constexpr int kSegBytes = 96;   // bytes of a 32-pixel row segment
+    static constexpr int kDtype = BEVK_U8;
+    using Reg = Pix;
+    using Out = uint32_t;                  // [c0, c1, c2, 0]
+    struct Store {
+        uint32_t sel_pack;  // PRMT selector that packs this lane's word out of (own, next lane's) pixel
+    };
+
+    // per-pixel registers from the clamped window: A = byte offset of its first byte inside the
+    // stage (or the frame), wc / wr = integer weights (0..32) of the two window columns / rows
+    template <bool LINEAR>
+    static __device__ __forceinline__ Reg make(bool act, uint32_t A, int wc0, int wc1, int wr0, int wr1)
+    {
+        Reg q;
+        q.addr = A & ~3u;
+        q.sh = 8 * (A & 3);
+        if (LINEAR) {
+            q.w03 = wc0 | (wc1 << 24);
+            q.w16 = wc0 | (wc1 << 16);
+            q.b0 = wr0 * 64;
+            q.b1 = wr1 * 64;
+        } else {
+            q.w03 = act ? 0x00ffffffu : 0u;
+            q.w16 = q.b0 = q.b1 = 0;
+        }
+        return q;
+    }
+    // window words per row that are always needed / offset of the last one, which only some
+    // alignments need (the direct-gather fallback clamps that one into the frame)
+    template <bool LINEAR> static constexpr int last_word_offset() { return LINEAR ? 8 : 4; }
+
+    template <bool LINEAR, typename LD>
+    static __device__ __forceinline__ void load(const Reg &q, uint32_t ra, uint32_t rb, uint32_t last_a,
+                                                uint32_t last_b, uint32_t (&w)[8], LD ld)
+    {
+        // ra / rb: address of the first window word in row 0 / 1; last_a / last_b: address of the
+        // last word of each row (ra + 8 unless the caller had to clamp it)
+        w[0] = ld(ra);
+        if (LINEAR) {
+            w[1] = ld(ra + 4);
+            w[2] = ld(last_a);
+            w[3] = ld(rb);
+            w[4] = ld(rb + 4);
+            w[5] = ld(last_b);
+        } else {
+            w[1] = ld(last_a);
+        }
+    }
+    template <bool LINEAR>
+    static __device__ __forceinline__ Out math(const Reg &q, const uint32_t (&w)[8])
+    {
+        if (LINEAR)  // byte-align the window of both rows, then interpolate
+            return lerp_aligned(q, __funnelshift_r(w[0], w[1], q.sh), __funnelshift_r(w[1], w[2], q.sh),
+                                __funnelshift_r(w[3], w[4], q.sh), __funnelshift_r(w[4], w[5], q.sh));
+        return __funnelshift_r(w[0], w[1], q.sh) & q.w03;
+    }
+
+    // Lanes 4j..4j+2 write words 3j..3j+2 of a 96-byte segment (32 pixels).
+    static __device__ __forceinline__ Store store_setup(int lane)
+    {
+        const int r4 = lane & 3;
+        Store s;
+        s.sel_pack = r4 == 0 ? 0x4210u : (r4 == 1 ? 0x5421u : 0x6542u);
+        return s;
+    }
+    static __device__ __forceinline__ uint32_t lane_offset(int lane) { return (3 * (lane >> 2) + (lane & 3)) * 4; }
+    // does this lane store for a segment with `valid_px` pixels (a multiple of 4)?
+    static __device__ __forceinline__ bool lane_stores(int lane, int valid_px)
+    {
+        return (lane & 3) < 3 && 4 * (lane >> 2) < valid_px;
+    }
+    static __device__ __forceinline__ void store(uint8_t *d, Out v, bool ok, const Store &s, int)
+    {
+        const uint32_t word = prmt(v, __shfl_down_sync(0xffffffffu, v, 1), s.sel_pack);
+        if (ok) st_stream(reinterpret_cast<uint32_t *>(d), word);
+    }
+    static __device__ __forceinline__ void store_zero(uint8_t *d, bool ok, int)
+    {
+        if (ok) st_stream(reinterpret_cast<uint32_t *>(d), 0u);
+    }
+};
