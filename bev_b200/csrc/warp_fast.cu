@@ -35,6 +35,7 @@
 // SURVEY.md 8d.
 #include "bevk_common.cuh"
 #include "warp_u8c3.cuh"
+#include "warp_f16c3.cuh"
 
 #include <cuda.h>  // CUtensorMap + enums only; the encoder is fetched through the runtime
 #include <mutex>
@@ -702,12 +703,12 @@ struct KernelConfig {
     int ring_bytes = 0;
 };
 constexpr int kMinCtas = 3;  // 80 registers per thread; the 64-register / 4-CTA build spills
-KernelConfig g_cfg[2][3];    // [linear][tile shape: SEGS 4, 2, 1]
+KernelConfig g_cfg[2][2][3];  // [pixel format: u8x3, f16x3][linear][tile shape: SEGS 4, 2, 1]
 inline int segs_index(int segs) { return segs == 4 ? 0 : (segs == 2 ? 1 : 2); }
 
-template <bool LINEAR, int SEGS> int configure(KernelConfig &cfg)
+template <typename PX, bool LINEAR, int SEGS> int configure(KernelConfig &cfg)
 {
-    auto kern = warp_fast_kernel<PxU8C3, LINEAR, kMinCtas, SEGS>;
+    auto kern = warp_fast_kernel<PX, LINEAR, kMinCtas, SEGS>;
     // how many CTAs the register file allows, then split the shared memory evenly between them
     BEVK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1024));
     int by_regs = 0;
@@ -731,17 +732,40 @@ template <bool LINEAR, int SEGS> int configure(KernelConfig &cfg)
     return BEVK_OK;
 }
 
-template <bool LINEAR> int configure_segs(int segs, KernelConfig &cfg)
+template <typename PX, bool LINEAR> int configure_segs(int segs, KernelConfig &cfg)
 {
-    return segs == 4 ? configure<LINEAR, 4>(cfg) : (segs == 2 ? configure<LINEAR, 2>(cfg) : configure<LINEAR, 1>(cfg));
+    return segs == 4 ? configure<PX, LINEAR, 4>(cfg)
+                     : (segs == 2 ? configure<PX, LINEAR, 2>(cfg) : configure<PX, LINEAR, 1>(cfg));
+}
+template <typename PX> int configure_any(int linear, int segs, KernelConfig &cfg)
+{
+    return linear ? configure_segs<PX, true>(segs, cfg) : configure_segs<PX, false>(segs, cfg);
 }
 
-template <bool LINEAR, int SEGS>
+template <typename PX, bool LINEAR, int SEGS>
 void launch(int grid, int smem, cudaStream_t stream, const BevkWarpParams &p, const WarpFastMaps &maps,
             const ChunkPlan &plan, int tiles_x, int tiles_y, int items, int ring_bytes, int *counter)
 {
-    warp_fast_kernel<PxU8C3, LINEAR, kMinCtas, SEGS><<<grid, kThreads, smem, stream>>>(
+    warp_fast_kernel<PX, LINEAR, kMinCtas, SEGS><<<grid, kThreads, smem, stream>>>(
         p, maps, plan, tiles_x, tiles_y, items, ring_bytes, counter);
+}
+template <typename PX>
+void launch_any(int linear, int segs, int grid, int smem, cudaStream_t stream, const BevkWarpParams &p,
+                const WarpFastMaps &maps, const ChunkPlan &plan, int tiles_x, int tiles_y, int items,
+                int ring_bytes, int *counter)
+{
+#define BEVK_LAUNCH(LIN, SEGS) \
+    launch<PX, LIN, SEGS>(grid, smem, stream, p, maps, plan, tiles_x, tiles_y, items, ring_bytes, counter)
+    if (linear) {
+        if (segs == 4) BEVK_LAUNCH(true, 4);
+        else if (segs == 2) BEVK_LAUNCH(true, 2);
+        else BEVK_LAUNCH(true, 1);
+    } else {
+        if (segs == 4) BEVK_LAUNCH(false, 4);
+        else if (segs == 2) BEVK_LAUNCH(false, 2);
+        else BEVK_LAUNCH(false, 1);
+    }
+#undef BEVK_LAUNCH
 }
 
 // ---- host side: which tile shape stages --------------------------------------------------------
@@ -749,7 +773,7 @@ void launch(int grid, int smem, cudaStream_t stream, const BevkWarpParams &p, co
 // widest tensor box, taller than kMaxBoxes boxes, or larger than half the ring.  The box of a tile
 // is spanned by its four corner pixels (a projective map is monotone along lines as long as w
 // keeps its sign); tiles where w changes sign are left out of the estimate (the kernel copes).
-double unstaged_fraction(const BevkWarpParams &p, int linear, int segs, int ring_bytes)
+double unstaged_fraction(const BevkWarpParams &p, int linear, int bpp, int segs, int ring_bytes)
 {
     const int tw = tile_w(segs), th = tile_h(segs);
     const int tiles_x = (p.dst_w + tw - 1) / tw, tiles_y = (p.dst_h + th - 1) / th;
@@ -789,8 +813,8 @@ double unstaged_fraction(const BevkWarpParams &p, int linear, int segs, int ring
                 lo_y = lo_y < 0 ? 0 : lo_y;
                 hi_x = hi_x > p.src_w - 1 ? p.src_w - 1 : hi_x;
                 hi_y = hi_y > p.src_h - 1 ? p.src_h - 1 : hi_y;
-                const int a0 = (3 * lo_x) & ~15;
-                const int need_w = ((3 * (hi_x + 1) + 15) & ~15) - a0 + 16;  // one chunk of margin
+                const int a0 = (bpp * lo_x) & ~15;
+                const int need_w = ((bpp * (hi_x + 1) + 15) & ~15) - a0 + 16;  // one chunk of margin
                 const int rows = hi_y - lo_y + 1 + 1;
                 const int pitch = need_w <= kMaxBoxWidth ? map_width(map_width_index(need_w)) : need_w;
                 if (need_w > kMaxBoxWidth || rows > kMaxBoxes * kMaxBoxHeight ||
@@ -803,7 +827,7 @@ double unstaged_fraction(const BevkWarpParams &p, int linear, int segs, int ring
 
 struct ModeKey {
     double M[BEVK_MAX_GROUPS][9];
-    int n_groups, src_h, src_w, dst_h, dst_w, linear;
+    int n_groups, src_h, src_w, dst_h, dst_w, linear, bpp;
 };
 struct ModeEntry {
     ModeKey key;
@@ -818,7 +842,7 @@ unsigned long long g_mode_stamp = 0;
 // Largest tile shape whose boxes all stage; 0 if even the best shape leaves more than
 // kMaxUnstaged of the tiles to the in-kernel fallback (strong minification: the boxes are mostly
 // untouched pixels, the direct-gather kernel moves less data).
-int pick_tile_shape(const BevkWarpParams &p, int linear, int ring_bytes, bool force)
+int pick_tile_shape(const BevkWarpParams &p, int linear, int bpp, int ring_bytes, bool force)
 {
     // nearest reads one tap per pixel, so its in-kernel fallback costs little: keep wide tiles
     constexpr double kMaxUnstaged = 0.05;
@@ -832,6 +856,7 @@ int pick_tile_shape(const BevkWarpParams &p, int linear, int ring_bytes, bool fo
     key.dst_h = p.dst_h;
     key.dst_w = p.dst_w;
     key.linear = linear;
+    key.bpp = bpp;
     std::lock_guard<std::mutex> lock(g_map_mutex);
     ModeEntry *victim = &g_mode_cache[0];  // an empty entry (stamp 0), else the least recently used
     for (int i = 0; i < kModeCacheSize; ++i) {
@@ -849,7 +874,7 @@ int pick_tile_shape(const BevkWarpParams &p, int linear, int ring_bytes, bool fo
     const char *env = getenv("BEVK_FAST_SEGS");  // tuning aid: force a tile shape
     for (int si = 0; si < 3; ++si) {
         if (env && atoi(env) != shapes[si]) continue;
-        const double f = unstaged_fraction(p, linear, shapes[si], ring_bytes);
+        const double f = unstaged_fraction(p, linear, bpp, shapes[si], ring_bytes);
         if (f < best_frac - 1e-9) {
             best_frac = f;
             best = shapes[si];
@@ -869,18 +894,21 @@ int pick_tile_shape(const BevkWarpParams &p, int linear, int ring_bytes, bool fo
 int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, int linear, int force,
                           cudaStream_t stream)
 {
-    // qualification: uint8 x 3, zero border, rows the tensor maps / word stores can address,
-    // per-frame dst pointer steps that fit 32 bits
-    if (dtype != BEVK_U8 || channels != 3) return 0;
+    // qualification: uint8 x 3 or float16 x 3, zero border, rows the tensor maps / word stores
+    // can address, per-frame dst pointer steps that fit 32 bits
+    if (channels != 3 || (dtype != BEVK_U8 && dtype != BEVK_F16)) return 0;
+    const int fmt = dtype == BEVK_F16 ? 1 : 0;
+    const int bpp = fmt ? PxF16C3::kBpp : PxU8C3::kBpp;
     if (p_in.border[0] != 0.f || p_in.border[1] != 0.f || p_in.border[2] != 0.f) return 0;
     if (p_in.src_w < 2 || p_in.src_h < 2) return 0;
-    if ((p_in.src_w * 3) % 16 != 0 || (p_in.dst_w % 4) != 0) return 0;
+    if ((p_in.src_w * bpp) % 16 != 0 || (p_in.dst_w % 4) != 0) return 0;
     if (((uintptr_t)p_in.src % 16) != 0 || ((uintptr_t)p_in.dst % 4) != 0) return 0;
 
     BevkWarpParams p = p_in;
     int n_src_frames = 0, max_count = 0;
     for (int i = 0; i < p.n_groups; ++i)
-        if ((long long)p.g[i].stride * p.dst_frame_elems > 0xffffffffLL || p.g[i].stride < 1) return 0;
+        if ((long long)p.g[i].stride * p.dst_frame_elems * (fmt ? 2 : 1) > 0xffffffffLL || p.g[i].stride < 1)
+            return 0;
     for (int i = 0; i < p.n_groups; ++i) {
         const int last = p.g[i].first + (p.g[i].count - 1) * p.g[i].stride;
         n_src_frames = n_src_frames > last + 1 ? n_src_frames : last + 1;
@@ -894,21 +922,21 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
     if (rows > 0x7fffffffLL) return 0;  // TMA coordinates are int32
 
     // tile shape: every shape's kernel has the same ring size, so configure the widest first
-    KernelConfig &cfg0 = g_cfg[linear ? 1 : 0][0];
+    KernelConfig &cfg0 = g_cfg[fmt][linear ? 1 : 0][0];
     if (!cfg0.ready) {
-        int rc = linear ? configure_segs<true>(4, cfg0) : configure_segs<false>(4, cfg0);
+        int rc = fmt ? configure_any<PxF16C3>(linear, 4, cfg0) : configure_any<PxU8C3>(linear, 4, cfg0);
         if (rc) return rc;
     }
-    const int segs = pick_tile_shape(p, linear, cfg0.ring_bytes, force != 0);
+    const int segs = pick_tile_shape(p, linear, bpp, cfg0.ring_bytes, force != 0);
     if (segs == 0) return 0;
-    KernelConfig &cfg = g_cfg[linear ? 1 : 0][segs_index(segs)];
+    KernelConfig &cfg = g_cfg[fmt][linear ? 1 : 0][segs_index(segs)];
     if (!cfg.ready) {
-        int rc = linear ? configure_segs<true>(segs, cfg) : configure_segs<false>(segs, cfg);
+        int rc = fmt ? configure_any<PxF16C3>(linear, segs, cfg) : configure_any<PxU8C3>(linear, segs, cfg);
         if (rc) return rc;
     }
 
     WarpFastMaps maps;
-    int rc = get_maps(p.src, p.src_w * 3, rows, maps);
+    int rc = get_maps(p.src, p.src_w * bpp, rows, maps);
     if (rc) return rc;
 
     const int tiles_x = (p.dst_w + tile_w(segs) - 1) / tile_w(segs);
@@ -958,18 +986,12 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
     if (counter) BEVK_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));
 
     const int smem = cfg.ring_bytes + kBarBytes + kTailSlack;
-#define BEVK_LAUNCH(LIN, SEGS) \
-    launch<LIN, SEGS>(grid, smem, stream, p, maps, plan, tiles_x, tiles_y, (int)items, cfg.ring_bytes, counter)
-    if (linear) {
-        if (segs == 4) BEVK_LAUNCH(true, 4);
-        else if (segs == 2) BEVK_LAUNCH(true, 2);
-        else BEVK_LAUNCH(true, 1);
-    } else {
-        if (segs == 4) BEVK_LAUNCH(false, 4);
-        else if (segs == 2) BEVK_LAUNCH(false, 2);
-        else BEVK_LAUNCH(false, 1);
-    }
-#undef BEVK_LAUNCH
+    if (fmt)
+        launch_any<PxF16C3>(linear, segs, grid, smem, stream, p, maps, plan, tiles_x, tiles_y, (int)items,
+                            cfg.ring_bytes, counter);
+    else
+        launch_any<PxU8C3>(linear, segs, grid, smem, stream, p, maps, plan, tiles_x, tiles_y, (int)items,
+                           cfg.ring_bytes, counter);
     BEVK_CUDA(cudaGetLastError());
     return 1;
 }

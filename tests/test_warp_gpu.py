@@ -216,15 +216,17 @@ def test_calibration_object_wrappers():
     assert tuple(img.shape) == (2, 1080, 1920, 3)
 
 
+@pytest.mark.parametrize("dtype", ["uint8", "float16"])
 @pytest.mark.parametrize("flags", [0, 1])
-def test_staged_kernel_box_shapes(flags):
-    """Shapes that push the staged kernel through every staging mode: one tensor box, several
-    boxes per frame (tall source boxes), boxes too wide / large for the ring (direct global loads
-    inside the same kernel), partial tiles, and frame counts that do not fill the ring stages."""
+def test_staged_kernel_box_shapes(flags, dtype):
+    """Shapes that push the staged kernel (both pixel formats) through every staging mode: one
+    tensor box, several boxes per frame (tall source boxes), boxes too wide / large for the ring
+    (direct global loads inside the same kernel), partial tiles, and frame counts that do not fill
+    the ring stages."""
     _native.set_warp_path("fast")
     try:
         rng = np.random.default_rng(5)
-        frames = np.stack([util.seeded_frame(300 + i, 540, 960, 3, "uint8") for i in range(7)])
+        frames = np.stack([util.seeded_frame(300 + i, 540, 960, 3, dtype) for i in range(7)])
         quad = np.array([[0, 0], [959, 0], [959, 539], [0, 539]], np.float64)
         cases = [
             ((256, 256), 0.0),    # ~3.7x / 2.1x minification: wide boxes, ~17 rows
@@ -261,3 +263,26 @@ def test_cfg2_full_batch(flags):
     for i in (0, 77, 255):
         ref = wo.warp_perspective(frames[i].cpu().numpy(), H, (1024, 1024), flags)
         assert util.bits_equal(out[i].cpu().numpy(), ref), i
+
+
+@pytest.mark.parametrize("flags", [1, 0, 17])
+def test_float16_staged_batch(flags):
+    """float16 x 3 through the staged kernel (the fp16 leg of BASELINE configs[4], at 1/4 size):
+    == float16(oracle(float32(src))) bit for bit, batch of 21 frames, two homographies."""
+    _native.set_warp_path("fast")
+    try:
+        S = np.diag([0.5, 0.5, 1.0])
+        H = S @ util.h_canon() @ np.linalg.inv(S)  # 960x540 -> 512x512
+        H2 = np.array([[0.9, 0.08, 12.0], [-0.04, 1.05, 6.0], [2e-5, 1e-4, 1.0]])
+        frames = np.stack([util.seeded_frame(800 + i, 540, 960, 3, "float16") for i in range(21)])
+        idx = np.array([i % 2 for i in range(21)], np.int32)
+        Hs = np.stack([H, H2])
+        if flags & 16:
+            Hs = np.stack([np.linalg.inv(H), np.linalg.inv(H2)])
+        out = gpu_warp(frames, Hs, (512, 512), flags, mat_index=idx)
+        assert out.dtype == np.float16
+        for i in (0, 1, 10, 19, 20):
+            ref = wo.warp_perspective(frames[i], Hs[idx[i]], (512, 512), flags=flags)
+            assert util.bits_equal(out[i], ref), (flags, i)
+    finally:
+        _native.set_warp_path("auto")
