@@ -477,6 +477,9 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
             }
         const uint32_t frame_bytes = ((uint32_t)(box_rows * pitch) + 127u) & ~127u;
         staged = staged && 2 * frame_bytes <= (uint32_t)ring_bytes;
+        // nearest reads one pixel per dst pixel: where the map minifies, most of the box would be
+        // staged for nothing (and fetched from HBM for nothing) -- gather those tiles directly
+        if (!LINEAR && frame_bytes > 3u * 1024u * (uint32_t)kBpp) staged = false;
         // frames per stage: as many as still leave a ring of 4 stages
         const int fps = (4 * kMaxStageFrames * frame_bytes <= (uint32_t)ring_bytes)
                             ? kMaxStageFrames
