@@ -40,6 +40,7 @@ SIGNATURES = {
     "bevk_warp_set_path": (_c_int, [_c_int]),
     "bevk_warp_touched_pixels": (_c_i64, [_c_int, _c_int, _c_int, _c_int, _dp, _c_int, _ip]),
     "bevk_composite_u8c3": (_c_int, [_vp, _vp, _vp, _vp, _c_i64, _c_int, _vp]),
+    "bevk_composite_bev_u8c3": (_c_int, [_vp, _vp, _vp, _vp] + [_c_int] * 8 + [_dp, _dp, _c_int, _vp]),
     "bevk_pts_project": (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _dp, _vp]),
     "bevk_xywhr2xyxy": (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _dp, _vp]),
     "bevk_xy82xywhr": (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _dp, _vp]),
@@ -319,6 +320,46 @@ def composite_u8c3(bg, fg, fg_mask, bw_mode=False, out=None):
         rc = lib().bevk_composite_u8c3(_vp(bg.data_ptr()), _vp(fg.data_ptr()), _vp(fg_mask.data_ptr()),
                                        _vp(out.data_ptr()), n_pixels, int(bool(bw_mode)), _stream_ptr(bg))
     _check(rc, "bevk_composite_u8c3")
+    return out
+
+
+def composite_bev_fusable(bg, fg, dsize):
+    """Shapes bevk_composite_bev_u8c3 takes: all widths multiples of 4, sources at least 2x2."""
+    return (bg.shape[-2] % 4 == 0 and fg.shape[-2] % 4 == 0 and int(dsize[0]) % 4 == 0
+            and min(bg.shape[-3], bg.shape[-2], fg.shape[-3], fg.shape[-2]) >= 2)
+
+
+def composite_bev_u8c3(bg, fg, fg_mask, H_bg, H_fg, dsize, out=None):
+    """Fused warp + warp + warp + blend (bev/tool/compo.py:26-50).  bg: (Hb,Wb,3) or (N,Hb,Wb,3);
+    fg, fg_mask: (N,Hf,Wf,3) uint8 CUDA; H_bg, H_fg: forward 3x3 (or (N,3,3)) float64 on the host;
+    dsize = (width, height) of the BEV.  Returns (N, height, width, 3)."""
+    import torch
+    for name, t in (("bg", bg), ("fg", fg), ("fg_mask", fg_mask)):
+        _require_cuda(t, name)
+        if t.dtype != torch.uint8 or t.shape[-1] != 3:
+            raise TypeError("%s must be uint8 (..., 3), got %s %s" % (name, t.dtype, tuple(t.shape)))
+    if fg.dim() != 4 or tuple(fg.shape) != tuple(fg_mask.shape):
+        raise ValueError("fg and fg_mask must share one (N, H, W, 3) shape; got %s %s"
+                         % (tuple(fg.shape), tuple(fg_mask.shape)))
+    n = fg.shape[0]
+    if bg.dim() == 3:
+        bg = bg[None]
+    if bg.dim() != 4 or bg.shape[0] not in (1, n):
+        raise ValueError("bg must be (H, W, 3) or (N, H, W, 3) with N = %d; got %s" % (n, tuple(bg.shape)))
+    Hb = np.ascontiguousarray(np.asarray(_to_numpy(H_bg), np.float64).reshape(-1, 9))
+    Hf = np.ascontiguousarray(np.asarray(_to_numpy(H_fg), np.float64).reshape(-1, 9))
+    if Hb.shape[0] != Hf.shape[0] or Hb.shape[0] not in (1, n):
+        raise ValueError("need 1 or %d homography pairs, got %d / %d" % (n, Hb.shape[0], Hf.shape[0]))
+    bg, fg, fg_mask = bg.contiguous(), fg.contiguous(), fg_mask.contiguous()
+    w, h = int(dsize[0]), int(dsize[1])
+    if out is None:
+        out = torch.empty((n, h, w, 3), dtype=torch.uint8, device=fg.device)
+    with torch.cuda.device(fg.device):
+        rc = lib().bevk_composite_bev_u8c3(
+            _vp(bg.data_ptr()), _vp(fg.data_ptr()), _vp(fg_mask.data_ptr()), _vp(out.data_ptr()),
+            n, bg.shape[0], bg.shape[1], bg.shape[2], fg.shape[1], fg.shape[2], h, w,
+            _dptr(Hb), _dptr(Hf), Hb.shape[0], _stream_ptr(fg))
+    _check(rc, "bevk_composite_bev_u8c3")
     return out
 
 

@@ -116,6 +116,23 @@ int bevk_composite_u8c3(const void *bg, const void *fg, const void *fg_mask, voi
                         int64_t n_pixels, int bw_mode, void *stream);
 
 /*
+ * Fused BEV compositor: replaces composite_bev_img (bev/tool/compo.py:26-50) -- the three
+ * cv2.warpPerspective calls at compo.py:38,46,47 and the blend at :49 -- in one pass:
+ *     out[i] = blend(warp(bg[i or 0], H_bg[k]), warp(fg[i], H_fg[k]), warp(fg_mask[i], H_fg[k]))
+ * with k = 0 (n_mats == 1, one camera pair for the batch) or k = i (n_mats == n_frames).  Warps are
+ * bilinear, border 0, to a dst_w x dst_h BEV; H_bg / H_fg are HOST float64 [n_mats][9] FORWARD
+ * (image -> BEV) matrices exactly as the reference hands them to cv2.  bg is n_bg (1 or n_frames)
+ * frames of bg_h x bg_w x 3 bytes, fg and fg_mask n_frames frames of fg_h x fg_w x 3, out n_frames
+ * BEVs; device buffers, 4-byte aligned.  Results are bit-identical to the three-warp route.
+ * Widths (bg_w, fg_w, dst_w) must be multiples of 4; other shapes take bevk_warp_perspective +
+ * bevk_composite_u8c3 (BEVK_E_ARG says so).
+ */
+int bevk_composite_bev_u8c3(const void *bg, const void *fg, const void *fg_mask, void *out,
+                            int n_frames, int n_bg, int bg_h, int bg_w, int fg_h, int fg_w,
+                            int dst_h, int dst_w, const double *H_bg, const double *H_fg,
+                            int n_mats, void *stream);
+
+/*
  * Homogeneous point projection with divide.  Replaces rbox.pts_world_bev (bev/rbox.py:136-151)
  * and the cv2.perspectiveTransform call sites (bev/visualizer/rbox_vis.py:54,61,74).
  *   pts/out [n][dim], dim 2 (w = 1 implied, 2 columns out) or 3 (homogeneous in, 3 columns out,

@@ -52,3 +52,13 @@ def composite_bev_img(bg, fg, fg_mask, H_world2bev, H_img2world_fix, K, RT, x_si
     fg_bev = warp_oracle.warp_perspective(fg, H_img2bev_cam, (x_size, y_size))
     mask_bev = warp_oracle.warp_perspective(fg_mask, H_img2bev_cam, (x_size, y_size))
     return composite_reg_img(bg_bev, fg_bev, mask_bev), H_world2img_cam
+
+
+def blend_integer(bg, fg, fg_mask):
+    """The blend of compo.py:16-23 in integers: (fg*k + bg*(255-k) + 127) // 255, the quotient
+    taken as ((n + 1) * 0x10101) >> 24 -- the form the CUDA kernels evaluate
+    (bev_b200/csrc/compo.cu).  tests/test_oracle_compo.py proves it equal to composite_reg_img's
+    float64 expression on all 2^24 (bg, fg, mask) byte triples."""
+    k = fg_mask.astype(np.uint64)
+    n = fg.astype(np.uint64) * k + bg.astype(np.uint64) * (255 - k) + 127
+    return (((n + 1) * 65793) >> 24).astype(np.uint8)

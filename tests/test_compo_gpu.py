@@ -29,7 +29,7 @@ def test_blend_every_value_pair():
     """All 256 x 256 x 256 (bg, fg, mask) byte triples against the float64 numpy expression."""
     v = np.arange(256, dtype=np.uint8)
     bg, fg = np.meshgrid(v, v, indexing="ij")
-    for m in range(0, 256, 5):
+    for m in range(256):
         b3 = np.repeat(bg[..., None], 3, 2)
         f3 = np.repeat(fg[..., None], 3, 2)
         m3 = np.full_like(b3, m)
@@ -62,3 +62,85 @@ def test_argument_errors():
         compo.composite_reg_img(t, t[:2], t)
     with pytest.raises(TypeError):
         compo.composite_reg_img(t.float(), t, t)
+
+
+# ---- fused compositor (bevk_composite_bev_u8c3) vs three warps + blend vs the oracle ------------
+def _quad_h(rng, src_wh, dst_wh, jitter):
+    """Homography taking a jittered quad of the source onto the jittered dst rectangle."""
+    import cv2
+    sw, sh = src_wh
+    dw, dh = dst_wh
+    s = np.float32([[0, 0], [sw, 0], [sw, sh], [0, sh]]) + rng.uniform(-jitter, jitter, (4, 2)).astype(np.float32) * [sw, sh]
+    d = np.float32([[0, 0], [dw, 0], [dw, dh], [0, dh]]) + rng.uniform(-jitter, jitter, (4, 2)).astype(np.float32) * [dw, dh]
+    return cv2.getPerspectiveTransform(s.astype(np.float32), d.astype(np.float32)).astype(np.float64)
+
+
+def _oracle_batch(B, F, M, Hb, Hf, dsize):
+    from oracle import warp_oracle
+    out = []
+    for i in range(F.shape[0]):
+        b = B[i if B.shape[0] > 1 else 0]
+        hb = Hb[i if Hb.shape[0] > 1 else 0]
+        hf = Hf[i if Hf.shape[0] > 1 else 0]
+        out.append(co.composite_reg_img(warp_oracle.warp_perspective(b, hb, dsize),
+                                        warp_oracle.warp_perspective(F[i], hf, dsize),
+                                        warp_oracle.warp_perspective(M[i], hf, dsize)))
+    return np.stack(out)
+
+
+@pytest.mark.parametrize("n,n_bg,n_mats,bg_hw,fg_hw,dsize", [
+    (3, 3, 1, (60, 88), (60, 88), (64, 50)),      # shared cameras, a background per frame
+    (5, 1, 1, (72, 100), (40, 64), (96, 33)),     # one background, renders of another size
+    (4, 1, 4, (50, 64), (64, 48), (36, 70)),      # a rendering camera per frame
+    (2, 2, 2, (33, 12), (9, 8), (8, 9)),          # tiny frames: every window touches a border
+    (40, 1, 40, (24, 32), (24, 32), (32, 16)),    # more camera pairs than one launch carries
+])
+def test_fused_bev_composite(n, n_bg, n_mats, bg_hw, fg_hw, dsize):
+    rng = np.random.default_rng(n * 1000 + n_mats)
+    B = rng.integers(0, 256, (n_bg,) + bg_hw + (3,), dtype=np.uint8)
+    F = rng.integers(0, 256, (n,) + fg_hw + (3,), dtype=np.uint8)
+    M = np.repeat(rng.integers(0, 256, (n,) + fg_hw + (1,), dtype=np.uint8), 3, axis=3)
+    M[:, : fg_hw[0] // 3] = 255
+    Hb = np.stack([_quad_h(rng, bg_hw[::-1], dsize, 0.3) for _ in range(n_mats)])
+    Hf = np.stack([_quad_h(rng, fg_hw[::-1], dsize, 0.3) for _ in range(n_mats)])
+    ref = _oracle_batch(B, F, M, Hb, Hf, dsize)
+    fused = compo.composite_bev_batch(cu(B), cu(F), cu(M), Hb, Hf, dsize, fused=True).cpu().numpy()
+    assert np.array_equal(fused, ref)
+    unfused = compo.composite_bev_batch(cu(B), cu(F), cu(M), Hb, Hf, dsize, fused=False).cpu().numpy()
+    assert np.array_equal(unfused, ref)
+
+
+def test_fused_bev_composite_shape_rules():
+    """Widths that are not multiples of 4 take the three-warp route automatically; forcing the
+    fused kernel on them is an argument error, never a silent fallback."""
+    rng = np.random.default_rng(77)
+    B = rng.integers(0, 256, (1, 30, 41, 3), dtype=np.uint8)
+    F = rng.integers(0, 256, (2, 30, 41, 3), dtype=np.uint8)
+    M = rng.integers(0, 256, (2, 30, 41, 3), dtype=np.uint8)
+    H = _quad_h(rng, (41, 30), (37, 22), 0.2)
+    ref = _oracle_batch(B, F, M, H[None], H[None], (37, 22))
+    out = compo.composite_bev_batch(cu(B), cu(F), cu(M), H, H, (37, 22)).cpu().numpy()
+    assert np.array_equal(out, ref)
+    from bev_b200._native import NativeError
+    with pytest.raises(NativeError, match="multiples of 4"):
+        compo.composite_bev_batch(cu(B), cu(F), cu(M), H, H, (37, 22), fused=True)
+
+
+def test_fused_bev_composite_full_size():
+    """1080p renders over a 1080p background into a 1024^2 BEV: fused == three warps + blend."""
+    g = torch.Generator(device=DEV).manual_seed(5)
+    n = 6
+    B = torch.randint(0, 256, (1, 1080, 1920, 3), dtype=torch.uint8, device=DEV, generator=g)
+    F = torch.randint(0, 256, (n, 1080, 1920, 3), dtype=torch.uint8, device=DEV, generator=g)
+    M = torch.randint(0, 256, (n, 1080, 1920, 3), dtype=torch.uint8, device=DEV, generator=g)
+    Hb = util.h_canon()
+    rng = np.random.default_rng(9)
+    Hf = np.stack([_quad_h(rng, (1920, 1080), (1024, 1024), 0.15) for _ in range(n)])
+    Hbn = np.repeat(np.asarray(Hb, np.float64)[None], n, 0)
+    a = compo.composite_bev_batch(B, F, M, Hbn, Hf, (1024, 1024), fused=True)
+    b = compo.composite_bev_batch(B, F, M, Hbn, Hf, (1024, 1024), fused=False)
+    assert torch.equal(a, b)
+    a1 = compo.composite_bev_batch(B, F, M, Hb, Hf[0], (1024, 1024), fused=True)
+    b1 = compo.composite_bev_batch(B, F, M, Hb, Hf[0], (1024, 1024), fused=False)
+    assert torch.equal(a1, b1)
+    assert torch.equal(a1[0], a[0])

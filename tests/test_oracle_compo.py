@@ -31,3 +31,13 @@ def test_blend_edge_values():
     fg = np.array([[[255, 0, 8]]], np.uint8)
     assert np.array_equal(co.composite_reg_img(bg, fg, np.zeros_like(bg)), bg)
     assert np.array_equal(co.composite_reg_img(bg, fg, np.full_like(bg, 255)), fg)
+
+
+def test_integer_blend_is_the_float64_blend_for_every_byte_triple():
+    """The kernels blend in integers (compo.cu); this is the proof obligation: the integer form
+    equals the reference's float64 numpy expression for all 256^3 (bg, fg, mask) values."""
+    v = np.arange(256, dtype=np.uint8)
+    bg, fg = np.meshgrid(v, v, indexing="ij")
+    for k in range(256):
+        m = np.full_like(bg, k)
+        assert np.array_equal(co.blend_integer(bg, fg, m), co.composite_reg_img(bg, fg, m)), k

@@ -110,10 +110,47 @@ def cfg4(n_frames=1000, steps=3):
                                                          tot_bytes / (tot_ms * 1e-3) / 1e9 / peak))
 
 
+def compo_bench(n=64, steps=10):
+    """BEV compositing: n 1080p renders + masks over ONE 1080p background into
+    1024^2 BEVs, fused kernel against three warps + blend.  Algorithmic bytes: touched pixels of
+    the background once, of render and mask per frame, plus the composite written once."""
+    from bev_b200 import compo
+    dev = torch.device("cuda", 0)
+    peak, _ = bench.measured_peak()
+    g = torch.Generator(device=dev).manual_seed(1234)
+    ssize, dsize = (1920, 1080), (1024, 1024)
+    B = torch.randint(0, 256, (1, 1080, 1920, 3), dtype=torch.uint8, device=dev, generator=g)
+    F = torch.randint(0, 256, (n, 1080, 1920, 3), dtype=torch.uint8, device=dev, generator=g)
+    M = torch.randint(0, 256, (n, 1080, 1920, 3), dtype=torch.uint8, device=dev, generator=g)
+    H = bench.h_canon(1)
+    T, _, _ = _native.warp_touched_pixels(ssize, dsize, H, 1)
+    D = dsize[0] * dsize[1]
+    algo = 3 * (T + n * (2 * T + D))
+    for per_frame in (False, True):
+        Hb = np.repeat(H[None], n, 0) if per_frame else H
+        for fused in (True, False):
+            for _ in range(2):
+                out = compo.composite_bev_batch(B, F, M, Hb, Hb, dsize, fused=fused)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                out = compo.composite_bev_batch(B, F, M, Hb, Hb, dsize, fused=fused)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            print("compo x%d %s %s: %.3f ms %.0f Mpix/s frac %.3f" % (
+                n, "camera per frame" if per_frame else "shared cameras", "fused" if fused else "3 warps + blend",
+                ms, n * D / ms / 1e3, algo / (ms * 1e-3) / 1e9 / peak))
+            del out
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "cfg4":
         if len(sys.argv) > 3:
             _native.set_warp_path(sys.argv[3])
         cfg4(int(sys.argv[2]) if len(sys.argv) > 2 else 1000)
+    elif len(sys.argv) > 1 and sys.argv[1] == "compo":
+        compo_bench(int(sys.argv[2]) if len(sys.argv) > 2 else 64)
     else:
         main()
