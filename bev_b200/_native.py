@@ -39,6 +39,7 @@ SIGNATURES = {
     "bevk_warp_host_rows": (_c_int, [_c_int, _c_int, _c_int, _c_int, _dp, _c_int, _c_int, _ip]),
     "bevk_warp_set_path": (_c_int, [_c_int]),
     "bevk_warp_touched_pixels": (_c_i64, [_c_int, _c_int, _c_int, _c_int, _dp, _c_int, _ip]),
+    "bevk_resize": (_c_int, [_vp, _vp] + [_c_int] * 8 + [_vp]),
     "bevk_composite_u8c3": (_c_int, [_vp, _vp, _vp, _vp, _c_i64, _c_int, _vp]),
     "bevk_composite_bev_u8c3": (_c_int, [_vp, _vp, _vp, _vp] + [_c_int] * 8 + [_dp, _dp, _c_int, _vp]),
     "bevk_pts_project": (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _dp, _vp]),
@@ -299,6 +300,38 @@ def rows_op(name, x, in_cols, out_shape_tail, *extra, H=None, has_H=False):
         rc = getattr(lib(), name)(*args)
     _check(rc, name)
     return out
+
+
+def resize(src, dsize, interpolation=1, dst=None):
+    """cv2.resize(src, dsize) (INTER_LINEAR) on uint8 CUDA frames (H,W), (H,W,C) or (N,H,W,C);
+    dsize = (width, height).  Replaces the per-frame call at vis_homo.py:90."""
+    import torch
+    _require_cuda(src, "src")
+    if src.dtype != torch.uint8:
+        raise TypeError("resize: only uint8 frames are implemented, got %s" % (src.dtype,))
+    if src.dim() not in (2, 3, 4):
+        raise ValueError("resize: src must be (H,W), (H,W,C) or (N,H,W,C); got %s" % (tuple(src.shape),))
+    w, h = int(dsize[0]), int(dsize[1])
+    s4 = src.contiguous()
+    if src.dim() == 2:
+        s4 = s4[None, :, :, None]
+    elif src.dim() == 3:
+        s4 = s4[None]
+    n, sh, sw, c = s4.shape
+    if dst is None:
+        dst = torch.empty((n, h, w, c), dtype=torch.uint8, device=src.device)
+    elif tuple(dst.shape[-3:] if src.dim() != 2 else dst.shape[-2:]) != ((h, w, c) if src.dim() != 2 else (h, w)) \
+            or dst.dtype != torch.uint8 or not dst.is_contiguous() or dst.device != src.device:
+        raise ValueError("resize: dst must be a contiguous uint8 tensor of the output shape on src's device")
+    with torch.cuda.device(src.device):
+        rc = lib().bevk_resize(_vp(s4.data_ptr()), _vp(dst.data_ptr()), n, sh, sw, h, w, c, 0,
+                               int(interpolation), _stream_ptr(src))
+    _check(rc, "bevk_resize")
+    if src.dim() == 2:
+        return dst.reshape(h, w)
+    if src.dim() == 3:
+        return dst.reshape(h, w, c)
+    return dst
 
 
 def composite_u8c3(bg, fg, fg_mask, bw_mode=False, out=None):

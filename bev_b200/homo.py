@@ -236,3 +236,20 @@ def warp_bev_to_img(bev_frames, calib, bspec, flags=INTER_LINEAR):
     """Inverse BEV -> image warp (north_star extension; same kernel, H inverted on the host)."""
     H = np.linalg.inv(compose_H_bev_img(calib, bspec))
     return warp_perspective(bev_frames, H, (int(calib.u_size), int(calib.v_size)), flags=flags)
+
+
+def resize(src, dsize, dst=None, interpolation=INTER_LINEAR):
+    """Drop-in for ``cv2.resize(src, dsize)`` (default INTER_LINEAR, uint8) on CUDA tensors, batched:
+    the small-frame copy of the reference's frame loop (vis_homo.py:90).  src (H, W), (H, W, C)
+    or (N, H, W, C); dsize = (width, height).  Bit-identical to cv2 4.13."""
+    return _native.resize(src, dsize, interpolation, dst)
+
+
+def warp_small_img_to_bev(frames, calib, bspec, new_u, new_v, flags=INTER_LINEAR):
+    """The small-frame path of vis_homo.py:73-78,90-91 on a frame batch: resize to (new_u, new_v),
+    rescale the calibration with ``Calib.scale(align_corners=False)`` and warp the small frames
+    to the same BEV.  Returns (small_frames, bev_small)."""
+    calib_small = calib.scale(align_corners=False, new_u=new_u, new_v=new_v)
+    H_small = np.linalg.inv(bspec.gen_H_world_bev()).dot(calib_small.gen_H_world_img())
+    small = resize(frames, (int(new_u), int(new_v)))
+    return small, warp_perspective(small, H_small, (int(bspec.u_size), int(bspec.v_size)), flags=flags)

@@ -104,6 +104,16 @@ int64_t bevk_warp_touched_pixels(int src_h, int src_w, int dst_h, int dst_w, con
                                  int flags, int *row_range);
 
 /*
+ * Batched cv2.resize(img, (dst_w, dst_h)) with the default INTER_LINEAR on uint8 frames: replaces
+ * the per-frame call at vis_homo.py:90 (the small-frame path; its result feeds the warp at
+ * vis_homo.py:91 through the homography of Calib.scale(align_corners=False), bev/calib.py:142-198).
+ * src [n_frames][src_h][src_w][channels], dst [n_frames][dst_h][dst_w][channels], device buffers,
+ * channels 1..4, dtype BEVK_U8, interpolation BEVK_INTER_LINEAR.  Bit-identical to OpenCV 4.13.
+ */
+int bevk_resize(const void *src, void *dst, int n_frames, int src_h, int src_w, int dst_h,
+                int dst_w, int channels, int dtype, int interpolation, void *stream);
+
+/*
  * Alpha compositing of uint8 BGR frames, the blend behind the three warps of
  * bev/tool/compo.py:38,46,47 -- replaces composite_reg_img (bev/tool/compo.py:5-24):
  *     out = uint8(min(round_half_even(fg * (mask / 255) + bg * (1 - mask / 255)), 255))

@@ -14,6 +14,8 @@ Fixtures written:
   warp_small.npz  small cv2.warpPerspective cases (seeded inputs, stored outputs), all dtypes/flags
   warp_hash.json  sha256 of cv2 outputs for seeded full-size cases (inputs regenerated from seed)
   cfg4_cams.json  the 8 BrnoCompSpeed-shaped cameras of BASELINE configs[3]: H_bev_img + BEV size
+  resize_kat.json sha256 of cv2.resize (uint8, INTER_LINEAR) outputs on seeded frames + the
+                  small-frame chain of vis_homo.py:73-78,90-91 (Calib.scale -> H_bev_img_small)
 """
 import hashlib
 import json
@@ -351,6 +353,57 @@ def gen_rbox7():
     np.savez_compressed(os.path.join(OUT, "rbox7_kat.npz"), **out)
 
 
+RESIZE_CASES = [  # (src_h, src_w, channels, dst_w, dst_h)
+    (1080, 1920, 3, 852, 480),   # vis_homo.py:90 with the default --calib-new-u/v
+    (1080, 1920, 3, 960, 540),   # exact 2x (cv2 switches to its area path: same bytes)
+    (1080, 1920, 3, 1920, 1080), # identity
+    (720, 1280, 3, 852, 480),
+    (480, 640, 3, 1000, 700),    # upscale
+    (100, 100, 1, 200, 200),
+    (37, 53, 3, 20, 11),
+    (64, 48, 4, 33, 77),
+    (9, 7, 3, 31, 29),
+    (2, 2, 3, 5, 5),
+    (1, 1, 3, 4, 3),
+    (5, 1, 1, 3, 7),
+    (1, 9, 3, 4, 1),
+    (300, 200, 2, 100, 50),
+    (17, 1000, 3, 1000, 17),
+    (50, 50, 3, 49, 51),
+    (211, 173, 3, 97, 131),
+    (131, 97, 4, 211, 173),
+]
+
+
+def gen_resize():
+    """cv2.resize fixtures; the numpy oracle must reproduce every one before it is stored."""
+    from oracle import resize_oracle
+    cases = []
+    for i, (h, w, c, dw, dh) in enumerate(RESIZE_CASES):
+        seed = 9000 + i
+        src = seeded_frame(seed, h, w, c, "uint8")
+        ref = cv2.resize(src if c > 1 else src[:, :, 0], (dw, dh))
+        got = resize_oracle.resize(src if c > 1 else src[:, :, 0], (dw, dh))
+        assert np.array_equal(ref, got), ("oracle != cv2", h, w, c, dw, dh)
+        cases.append({"seed": seed, "shape": [h, w, c], "dsize": [dw, dh],
+                      "sha256": hashlib.sha256(np.ascontiguousarray(ref).tobytes()).hexdigest()})
+    # the small-frame chain of vis_homo.py:73-78,90-91 on cfg-4 camera 0
+    calib, bspec, _, _ = cfg4_camera(0)
+    new_u, new_v = 852, 480
+    calib_small = calib.scale(align_corners=False, new_u=new_u, new_v=new_v)
+    H_world_bev = bspec.gen_H_world_bev()
+    H_small = np.linalg.inv(H_world_bev).dot(calib_small.gen_H_world_img())
+    img = seeded_frame(9100, 1080, 1920, 3, "uint8")
+    small = cv2.resize(img, (new_u, new_v))
+    bev_small = cv2.warpPerspective(small, H_small, (bspec.u_size, bspec.v_size))
+    chain = {"seed": 9100, "new_uv": [new_u, new_v], "H_bev_img_small": L(H_small),
+             "bev_size": [int(bspec.u_size), int(bspec.v_size)],
+             "sha256_small": hashlib.sha256(small.tobytes()).hexdigest(),
+             "sha256_bev_small": hashlib.sha256(bev_small.tobytes()).hexdigest()}
+    with open(os.path.join(OUT, "resize_kat.json"), "w") as f:
+        json.dump({"cv2": cv2.__version__, "cases": cases, "small_frame_chain": chain}, f, indent=1)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1 and sys.argv[1] == "compo":
@@ -359,11 +412,15 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "rbox7":
         gen_rbox7()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "resize":
+        gen_resize()
+        sys.exit(0)
     gen_homo_kat()
     gen_cfg4()
     gen_rbox_kat()
     gen_warp()
     gen_compo()
     gen_rbox7()
+    gen_resize()
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))

@@ -145,11 +145,39 @@ def compo_bench(n=64, steps=10):
             del out
 
 
+def resize_bench(n=256, steps=10):
+    """cv2.resize of the reference's small-frame path (vis_homo.py:90): n 1080p BGR frames ->
+    852x480.  Algorithmic bytes: source pixels with a non-zero tap weight + the small frames."""
+    from oracle import resize_oracle
+    dev = torch.device("cuda", 0)
+    peak, _ = bench.measured_peak()
+    g = torch.Generator(device=dev).manual_seed(1234)
+    frames = torch.randint(0, 256, (n, 1080, 1920, 3), dtype=torch.uint8, device=dev, generator=g)
+    for dsize in ((852, 480), (960, 540), (1280, 720)):
+        out = torch.empty((n, dsize[1], dsize[0], 3), dtype=torch.uint8, device=dev)
+        T = resize_oracle.touched_pixels((1920, 1080), dsize)
+        algo = 3 * n * (T + dsize[0] * dsize[1])
+        for _ in range(3):
+            homo.resize(frames, dsize, dst=out)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            homo.resize(frames, dsize, dst=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        print("resize x%d 1080p -> %dx%d: %.3f ms %.0f Mpix/s (output) frac %.3f" % (
+            n, dsize[0], dsize[1], ms, n * dsize[0] * dsize[1] / ms / 1e3, algo / (ms * 1e-3) / 1e9 / peak))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "cfg4":
         if len(sys.argv) > 3:
             _native.set_warp_path(sys.argv[3])
         cfg4(int(sys.argv[2]) if len(sys.argv) > 2 else 1000)
+    elif len(sys.argv) > 1 and sys.argv[1] == "resize":
+        resize_bench(int(sys.argv[2]) if len(sys.argv) > 2 else 256)
     elif len(sys.argv) > 1 and sys.argv[1] == "compo":
         compo_bench(int(sys.argv[2]) if len(sys.argv) > 2 else 64)
     else:
