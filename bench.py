@@ -291,6 +291,7 @@ def ours(args, wl):
             "gpu_launches": args.steps * 1,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "frac_of_nominal_8000": achieved / 8000.0,
                          "algo_bytes_per_launch": algo_bytes_step,
                          "algo_bytes_per_frame": algo_bytes_frame,
                          "launch_ms": launch_ms, "kernel": "bevk warp kernel (1 launch per step)"},
