@@ -53,6 +53,8 @@ SIGNATURES = {
     "bevk_v2yaw": (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _vp]),
     "bevk_yaw2v": (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _vp]),
     "bevk_yaw2mat": (_c_int, [_vp, _vp, _c_i64, _c_int, _c_int, _vp]),
+    "bevk_rbox_iou_matrix": (_c_int, [_vp, _c_i64, _c_int, _vp, _c_i64, _c_int, _vp, _c_int,
+                                      ctypes.c_double, _vp]),
     "bevk_xywhr2xyxy_host": (_c_int, [_fp, _fp, _c_i64, _c_int, _dp]),
     "bevk_xy82xywhr_host": (_c_int, [_fp, _fp, _c_i64, _c_int, _dp]),
 }
@@ -413,4 +415,27 @@ def rbox_zt2tt_world(x, K, Rt):
         rc = lib().bevk_rbox_zt2tt_world(_vp(x2.data_ptr()), _vp(out.data_ptr()), x2.shape[0], code,
                                          _dptr(Kn), _dptr(Rn), _stream_ptr(x))
     _check(rc, "bevk_rbox_zt2tt_world")
+    return out
+
+
+def rbox_iou_matrix(boxes1, boxes2, yaw_offset=0.0):
+    """(N, >=5), (M, >=5) CUDA float32/float64 boxes [x, y, w, h, r, ...] -> (N, M) IoU matrix
+    (w along (cos r, sin r)); replaces d3d.box.box2d_iou(..., method="rbox")
+    (bev/tracker/rbox_tracker.py:87-92)."""
+    import torch
+    _require_cuda(boxes1, "boxes1")
+    _require_cuda(boxes2, "boxes2")
+    code = _proj_dtype(boxes1)
+    if boxes2.dtype != boxes1.dtype or boxes2.device != boxes1.device:
+        raise TypeError("boxes1 and boxes2 must share dtype and device")
+    for name, b in (("boxes1", boxes1), ("boxes2", boxes2)):
+        if b.dim() != 2 or b.shape[1] < 5:
+            raise ValueError("%s must be (N, >=5) rows [x, y, w, h, r, ...], got %s" % (name, tuple(b.shape)))
+    b1, b2 = boxes1.contiguous(), boxes2.contiguous()
+    out = torch.empty((b1.shape[0], b2.shape[0]), dtype=b1.dtype, device=b1.device)
+    with torch.cuda.device(b1.device):
+        rc = lib().bevk_rbox_iou_matrix(_vp(b1.data_ptr()), b1.shape[0], b1.shape[1], _vp(b2.data_ptr()),
+                                        b2.shape[0], b2.shape[1], _vp(out.data_ptr()), code,
+                                        float(yaw_offset), _stream_ptr(b1))
+    _check(rc, "bevk_rbox_iou_matrix")
     return out

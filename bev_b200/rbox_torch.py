@@ -13,6 +13,8 @@ tensors; homographies are host float64 3x3 (numpy or CPU tensor).  Coordinate co
   bev   : u right, v down; yaw 0 = +v, yaw = atan2(u, v); w along u, h along v
   world : right-handed x/y; yaw 0 = +x, yaw = atan2(y, x); h along x, w along y
 """
+import math
+
 from . import _native
 
 _MODES = ("bev", "world")
@@ -124,3 +126,18 @@ def rboxzt_world_bev(rbox_src, H, K, Rt, src):
     if src != "world":
         raise NotImplementedError("rboxzt_world_bev only supports converting from world to bev")
     return rboxtt_world_bev(rbox_zt2tt_world(rbox_src, K, Rt), H, src)
+
+
+# ---- rotated-box IoU: the tracker's association matrix -------------------------
+def box2d_iou(boxes1, boxes2, method="rbox"):
+    """Drop-in for the one d3d call of the reference, ``d3d.box.box2d_iou(boxes1, boxes2,
+    method="rbox")`` (bev/tracker/rbox_tracker.py:92): (N, >=5) x (M, >=5) boxes [x, y, w, h, r]
+    -> (N, M) IoU matrix, w along (cos r, sin r).  CUDA float32 / float64 tensors."""
+    assert method == "rbox", "only the rotated-box IoU the reference uses is implemented"
+    return _native.rbox_iou_matrix(boxes1, boxes2, 0.0)
+
+
+def iou_batch_rbox(bb_test, bb_gt):
+    """rbox_tracker.py:87-92: IoU matrix of detections (N, >=5) against trackers (M, >=5), both
+    [x, y, w, h, r, ...], yaw shifted by pi/2 exactly as the reference does before calling d3d."""
+    return _native.rbox_iou_matrix(bb_test, bb_gt, math.pi / 2)

@@ -208,6 +208,18 @@ int bevk_yaw2mat(const void *yaw, void *mat, int64_t n, int mode, int dtype, voi
 int bevk_xywhr2xyxy_host(const float *xywhr, float *xy8, int64_t n, int mode, const double *H);
 int bevk_xy82xywhr_host(const float *xy8, float *xywhr, int64_t n, int mode, const double *H);
 
+/*
+ * Rotated-box IoU matrix: replaces d3d.box.box2d_iou(boxes1, boxes2, method="rbox") as called by
+ * iou_batch_rbox (bev/tracker/rbox_tracker.py:87-92; association step :383-405).
+ *   boxes1 [n] rows of stride1 elements, boxes2 [m] rows of stride2 elements (stride >= 5, so
+ *   detections carrying a score column need no copy); the first five are [x, y, w, h, r]:
+ *   centre, side w along (cos r, sin r), side h along (-sin r, cos r).  yaw_offset is added to
+ *   every r (the reference passes r + pi/2).  out [n][m], IoU = |A n B| / (|A| + |B| - |A n B|).
+ *   dtype BEVK_F32 | BEVK_F64 (boxes and out); device buffers.
+ */
+int bevk_rbox_iou_matrix(const void *boxes1, int64_t n, int stride1, const void *boxes2, int64_t m,
+                         int stride2, void *out, int dtype, double yaw_offset, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,8 @@ Fixtures written:
   warp_small.npz  small cv2.warpPerspective cases (seeded inputs, stored outputs), all dtypes/flags
   warp_hash.json  sha256 of cv2 outputs for seeded full-size cases (inputs regenerated from seed)
   cfg4_cams.json  the 8 BrnoCompSpeed-shaped cameras of BASELINE configs[3]: H_bev_img + BEV size
+  iou_kat.npz     rotated-box pairs with cv2.rotatedRectangleIntersection areas (float32 inside
+                  OpenCV) next to the float64 IoU oracle's values, incl. degenerate pairs
   resize_kat.json sha256 of cv2.resize (uint8, INTER_LINEAR) outputs on seeded frames + the
                   small-frame chain of vis_homo.py:73-78,90-91 (Calib.scale -> H_bev_img_small)
 """
@@ -404,6 +406,44 @@ def gen_resize():
         json.dump({"cv2": cv2.__version__, "cases": cases, "small_frame_chain": chain}, f, indent=1)
 
 
+def gen_iou():
+    """Rotated-box IoU fixtures: the float64 oracle is checked against OpenCV's own rotated
+    rectangle intersection (third party, float32) before its values are stored."""
+    from oracle import iou_oracle
+    rng = np.random.default_rng(77)
+    n = 400
+    b1 = np.stack([rng.uniform(0, 60, n), rng.uniform(0, 60, n), rng.uniform(1.5, 20, n),
+                   rng.uniform(1.5, 20, n), rng.uniform(-np.pi, np.pi, n)], 1)
+    b2 = b1.copy()
+    b2[:, :2] += rng.normal(0, 5, (n, 2))
+    b2[:, 2:4] = rng.uniform(1.5, 20, (n, 2))
+    b2[:, 4] = rng.uniform(-np.pi, np.pi, n)
+    b2[::10] = b1[::10]                      # identical boxes
+    b2[1::10] = b1[1::10]
+    b2[1::10, 0] += 1.0                      # shifted copies: coincident edge lines
+    b2[2::10, :2] = b1[2::10, :2] + 100      # far apart
+    b1 = b1.astype(np.float32).astype(np.float64)   # exactly representable in float32
+    b2 = b2.astype(np.float32).astype(np.float64)
+    inter_cv = np.zeros(n)
+    inter_or = np.zeros(n)
+    for i in range(n):
+        r1 = ((b1[i, 0], b1[i, 1]), (b1[i, 2], b1[i, 3]), float(np.degrees(b1[i, 4])))
+        r2 = ((b2[i, 0], b2[i, 1]), (b2[i, 2], b2[i, 3]), float(np.degrees(b2[i, 4])))
+        ret, pts = cv2.rotatedRectangleIntersection(r1, r2)
+        if ret != 0 and pts is not None and len(pts) >= 3:
+            inter_cv[i] = cv2.contourArea(cv2.convexHull(pts))
+        inter_or[i] = iou_oracle.intersection_area(b1[i], b2[i])
+    scale = np.maximum(b1[:, 2] * b1[:, 3], b2[:, 2] * b2[:, 3])
+    assert np.all(np.abs(inter_cv - inter_or) <= 5e-4 * scale), float(np.max(np.abs(inter_cv - inter_or) / scale))
+    iou_pairs = np.array([iou_oracle.box2d_iou(b1[i:i + 1], b2[i:i + 1])[0, 0] for i in range(n)])
+    dets = np.concatenate([b1[:24], rng.uniform(0, 1, (24, 1))], 1)   # (24, 6): with a score column
+    trks = b2[:17]
+    np.savez_compressed(os.path.join(OUT, "iou_kat.npz"), b1=b1, b2=b2, inter_cv=inter_cv,
+                        iou_pairs=iou_pairs, dets=dets, trks=trks,
+                        iou_matrix=iou_oracle.box2d_iou(dets, trks),
+                        iou_tracker=iou_oracle.iou_batch_rbox(dets, trks))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1 and sys.argv[1] == "compo":
@@ -411,6 +451,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "rbox7":
         gen_rbox7()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "iou":
+        gen_iou()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "resize":
         gen_resize()
@@ -422,5 +465,6 @@ if __name__ == "__main__":
     gen_compo()
     gen_rbox7()
     gen_resize()
+    gen_iou()
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))

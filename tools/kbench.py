@@ -171,11 +171,39 @@ def resize_bench(n=256, steps=10):
             n, dsize[0], dsize[1], ms, n * dsize[0] * dsize[1] / ms / 1e3, algo / (ms * 1e-3) / 1e9 / peak))
 
 
+def iou_bench(n=8192, steps=10):
+    """Rotated-box IoU matrix (tracker association, rbox_tracker.py:87-92): n x n float32 boxes.
+    Compute-bound (float64 registers); the HBM figure is the n^2 * 4 B matrix it writes."""
+    from bev_b200 import rbox_torch
+    dev = torch.device("cuda", 0)
+    peak, _ = bench.measured_peak()
+    g = torch.Generator(device=dev).manual_seed(3)
+    u = torch.rand((2, n, 5), device=dev, generator=g)
+    lo = torch.tensor([0.0, 0.0, 1.0, 1.0, -3.2], device=dev)
+    hi = torch.tensor([300.0, 300.0, 30.0, 30.0, 3.2], device=dev)
+    a, b = (lo + u[0] * (hi - lo)).contiguous(), (lo + u[1] * (hi - lo)).contiguous()
+    for _ in range(3):
+        out = rbox_torch.iou_batch_rbox(a, b)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = rbox_torch.iou_batch_rbox(a, b)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    print("iou %d x %d: %.3f ms %.1f Gpairs/s, matrix written at %.0f GB/s (%.2f of the HBM peak), %.1f %% pairs overlap"
+          % (n, n, ms, n * n / ms / 1e6, n * n * 4 / ms / 1e6, n * n * 4 / ms / 1e6 / peak,
+             100.0 * float((out > 0).float().mean())))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "cfg4":
         if len(sys.argv) > 3:
             _native.set_warp_path(sys.argv[3])
         cfg4(int(sys.argv[2]) if len(sys.argv) > 2 else 1000)
+    elif len(sys.argv) > 1 and sys.argv[1] == "iou":
+        iou_bench(int(sys.argv[2]) if len(sys.argv) > 2 else 8192)
     elif len(sys.argv) > 1 and sys.argv[1] == "resize":
         resize_bench(int(sys.argv[2]) if len(sys.argv) > 2 else 256)
     elif len(sys.argv) > 1 and sys.argv[1] == "compo":
