@@ -285,6 +285,29 @@ struct FnYaw2mat {  // rbox_torch.py:42-50
     }
 };
 
+struct FnAngle {  // angle_world_bev: yaw2v(src) -> H[:2,:2] . v -> v2yaw(target)      rbox.py:162-171
+    static constexpr int IN = 1, OUT = 1;
+    double h00, h01, h10, h11;
+    int src_mode;
+    template <typename T> __device__ __forceinline__ void operator()(const double *in, double *out) const
+    {
+        double s, c;
+        Tr<T>::sincos(in[0], s, c);
+        const double vx = (src_mode == BEVK_MODE_BEV) ? s : c;
+        const double vy = (src_mode == BEVK_MODE_BEV) ? c : s;
+        const double tx = fma(h00, vx, h01 * vy), ty = fma(h10, vx, h11 * vy);
+        out[0] = (src_mode == BEVK_MODE_BEV) ? Tr<T>::atan2(ty, tx) : Tr<T>::atan2(tx, ty);
+    }
+};
+struct FnDist {  // dist_world_bev: lengths times the similarity's scale                rbox.py:153-160
+    static constexpr int IN = 1, OUT = 1;
+    double scale;
+    template <typename T> __device__ __forceinline__ void operator()(const double *in, double *out) const
+    {
+        out[0] = in[0] * scale;
+    }
+};
+
 // ---- the row kernel -----------------------------------------------------------------------------
 template <typename T, typename F>
 __global__ void __launch_bounds__(kRows) rows_kernel(const T *__restrict__ in, T *__restrict__ out,
@@ -631,6 +654,33 @@ int bevk_rbox_zt2tt_world(const void *in, void *out, int64_t n, int dtype, const
     }
     if (!bevk_invert3x3(Hcw, f.Hwc.h)) BEVK_FAIL(BEVK_E_ARG, "bevk_rbox_zt2tt_world: K [r1 r2 t] is singular");
     return launch_rows(in, out, n, dtype, f, (cudaStream_t)stream, "bevk_rbox_zt2tt_world");
+}
+
+int bevk_angle_world_bev(const void *yaw_in, void *yaw_out, int64_t n, int src_mode, int dtype,
+                         const double H[9], void *stream)
+{
+    if (int rc = check_mode(src_mode, "bevk_angle_world_bev")) return rc;
+    if (!H) BEVK_FAIL(BEVK_E_ARG, "bevk_angle_world_bev: H is null");
+    FnAngle f;
+    f.h00 = H[0];
+    f.h01 = H[1];
+    f.h10 = H[3];
+    f.h11 = H[4];
+    f.src_mode = src_mode;
+    return launch_rows(yaw_in, yaw_out, n, dtype, f, (cudaStream_t)stream, "bevk_angle_world_bev");
+}
+
+int bevk_dist_world_bev(const void *dist_in, void *dist_out, int64_t n, int dtype, const double H[9],
+                        void *stream)
+{
+    if (!H) BEVK_FAIL(BEVK_E_ARG, "bevk_dist_world_bev: H is null");
+    // the numpy twin compares COLUMN norms (rbox.py:154-156)
+    const double s0 = sqrt(H[0] * H[0] + H[3] * H[3]), s1 = sqrt(H[1] * H[1] + H[4] * H[4]);
+    if (!(fabs(s0 - s1) < 1e-5))
+        BEVK_FAIL(BEVK_E_AFFINE, "bevk_dist_world_bev: H is not a similarity (scales %g vs %g)", s0, s1);
+    FnDist f;
+    f.scale = s0;
+    return launch_rows(dist_in, dist_out, n, dtype, f, (cudaStream_t)stream, "bevk_dist_world_bev");
 }
 
 int bevk_xywhr2xyvec(const void *xywhr, void *xyvec, int64_t n, int mode, int dtype, void *stream)

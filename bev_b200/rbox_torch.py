@@ -82,6 +82,18 @@ def pts_world_bev(pts_src, H):
     return _native.rows_op("bevk_pts_project", pts_src, dim, (dim,), dim, H=H, has_H=True)
 
 
+def dist_world_bev(dist_src, H):
+    """Lengths through a similarity H: ``sqrt(H00^2 + H10^2) * dist_src``, any shape (reference
+    rbox.py:153-160); AssertionError when H's two column norms differ, as there."""
+    return _native.rows_op("bevk_dist_world_bev", dist_src, 1, (), H=H, has_H=True).reshape(dist_src.shape)
+
+
+def angle_world_bev(angle_src, H, src):
+    """Yaw angles (any shape, flattened like the reference) from ``src`` to the other system
+    through H's upper-left 2x2 (reference rbox.py:162-171)."""
+    return _native.rows_op("bevk_angle_world_bev", angle_src, 1, (), _mode(src), H=H, has_H=True)
+
+
 def xy82xywhr(xy8, mode):
     """(N,8) corners -> (N,5) [x,y,w,h,yaw] (reference rbox.py:50-63)."""
     return _native.rows_op("bevk_xy82xywhr", xy8, 8, (5,), _mode(mode), H=None, has_H=True)

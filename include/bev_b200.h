@@ -195,6 +195,14 @@ int bevk_rbox_zt2tt_world(const void *rboxzt, void *rboxtt, int64_t n, int dtype
 
 /* Heading segments [n][4] = [x, y, x + h*dx, y + h*dy].  rbox_torch.xywhr2xyvec (:101-112). */
 int bevk_xywhr2xyvec(const void *xywhr, void *xyvec, int64_t n, int mode, int dtype, void *stream);
+/* Yaw angles through a similarity: yaw2v(src) -> H[:2,:2] . v -> v2yaw(other system).
+ * rbox.angle_world_bev (bev/rbox.py:162-171); H is used as given (not normalised), like there. */
+int bevk_angle_world_bev(const void *yaw_in, void *yaw_out, int64_t n, int src_mode, int dtype,
+                         const double H[9], void *stream);
+/* Lengths through a similarity: dist * sqrt(H00^2 + H10^2).  rbox.dist_world_bev
+ * (bev/rbox.py:153-160); BEVK_E_AFFINE when the two column norms differ by >= 1e-5 (its assert). */
+int bevk_dist_world_bev(const void *dist_in, void *dist_out, int64_t n, int dtype, const double H[9],
+                        void *stream);
 /* Heading segments from corners.  rbox_torch.xy82xyvec (:114-121). */
 int bevk_xy82xyvec(const void *xy8, void *xyvec, int64_t n, int dtype, void *stream);
 /* v [n][2] -> yaw [n].  rbox_torch.v2yaw (:24-31). */

@@ -183,3 +183,26 @@ def test_seven_dof_boxes():
     with pytest.raises(AssertionError):
         rt.rboxtt_world_bev(tt, util.h_canon(), "world")  # not affine
     assert tuple(rt.rboxtt_world_bev(torch.zeros((0, 7), device=DEV), K7["H"], "bev").shape) == (0, 7)
+
+
+@pytest.mark.parametrize("src", ["bev", "world"])
+def test_dist_and_angle_world_bev(src):
+    """Torch twins of rbox.dist_world_bev / angle_world_bev (bev/rbox.py:153-171)."""
+    rng = np.random.default_rng(21)
+    H = K["H_sim_a"]
+    d = rng.uniform(0.1, 80, (1000, 2)).astype(np.float32)
+    out = rt.dist_world_bev(cu(d), H)
+    assert tuple(out.shape) == (1000, 2)
+    assert util.rel_err(out.cpu().numpy(), ro.dist_world_bev(d, H)) <= TOL
+    yaw = rng.uniform(-7, 7, 3001).astype(np.float32)
+    got = rt.angle_world_bev(cu(yaw), H, src).cpu().numpy()
+    assert got.shape == (3001,)
+    assert util.yaw_err(got, ro.angle_world_bev(yaw, H, src)) <= TOL
+    # un-normalised H is used as given: a negative H22 keeps its sign, exactly as the numpy twin
+    got = rt.angle_world_bev(cu(yaw), -2.5 * H, src).cpu().numpy()
+    assert util.yaw_err(got, ro.angle_world_bev(yaw, -2.5 * H, src)) <= TOL
+    with pytest.raises(AssertionError):
+        rt.dist_world_bev(cu(d), np.diag([1.0, 2.0, 1.0]))
+    with pytest.raises(AssertionError):
+        rt.angle_world_bev(cu(yaw), H, "img")
+    assert tuple(rt.angle_world_bev(torch.zeros(0, device=DEV), H, src).shape) == (0,)
