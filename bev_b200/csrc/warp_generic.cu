@@ -199,21 +199,9 @@ __global__ void __launch_bounds__(256) warp_u8c3_direct_kernel(const __grid_cons
     const uint32_t row_bytes = (uint32_t)p.src_w * 3u;
     const uint32_t A = act ? (uint32_t)rs * row_bytes + 3u * (uint32_t)cs : 0u;
     const uint32_t last_word = (uint32_t)p.src_frame_elems - 4u;
-    Pix q;
-    q.addr = A & ~3u;
-    q.sh = 8 * (A & 3);
-    uint32_t off2;  // third (nearest: second) window word, clamped into the frame where unused
-    if (LINEAR) {
-        q.w03 = act ? (wc0 | (wc1 << 24)) : 0;
-        q.w16 = act ? (wc0 | (wc1 << 16)) : 0;
-        q.b0 = wr0 * 64;
-        q.b1 = wr1 * 64;
-        off2 = min(q.addr + 8u, last_word - row_bytes);
-    } else {
-        q.w03 = act ? 0x00ffffffu : 0u;
-        q.w16 = q.b0 = q.b1 = 0;
-        off2 = min(q.addr + 4u, last_word);
-    }
+    const Pix q = PxU8C3::make<LINEAR>(act, A, act ? wc0 : 0, act ? wc1 : 0, wr0, wr1);
+    // third (nearest: second) window word, clamped into the frame where unused
+    const uint32_t off2 = LINEAR ? min(q.addr + 8u, last_word - row_bytes) : min(q.addr + 4u, last_word);
     // lanes 4j..4j+2 write words 3j..3j+2 of the warp's 96-byte segment
     const int j = lane >> 2, r4 = lane & 3;
     const uint32_t sel_pack = r4 == 0 ? 0x4210u : (r4 == 1 ? 0x5421u : 0x6542u);
@@ -237,7 +225,7 @@ __global__ void __launch_bounds__(256) warp_u8c3_direct_kernel(const __grid_cons
         } else {
             const uint32_t r0 = __ldg((const uint32_t *)(s + q.addr));
             const uint32_t r1 = __ldg((const uint32_t *)(s + off2));
-            P = __funnelshift_r(r0, r1, q.sh) & q.w03;
+            P = __funnelshift_r(r0, r1, q.sh) & q.w0;
         }
         const uint32_t word = prmt(P, __shfl_down_sync(0xffffffffu, P, 1), sel_pack);
         if (st_ok) st_stream(reinterpret_cast<uint32_t *>(dst + fr * p.dst_frame_elems), word);

@@ -28,30 +28,33 @@ __device__ __forceinline__ void window(int s, int frac, int n, int &first, int &
 struct Pix {
     uint32_t addr;   // byte offset (4-aligned) inside a stage of the first window word, row 0
     uint32_t sh;     // 8 * (window start & 3): funnel-shift amount that byte-aligns the window
-    uint32_t w03;    // bilinear: column weights as bytes 0 and 3 (dp4a with [B0 B1 B2 B3] -> ch. 0)
+    uint32_t w0;     // bilinear: the two tap weights of window row 0 as 16-bit halves (dp2a operand)
                      // nearest : 0x00ffffff when the tap is inside the image, else 0
-    uint32_t w16;    // column weights as 16-bit halves (dp2a lo/hi with [B1 B4 B2 B5] -> ch. 1, 2)
-    uint32_t b0, b1; // row weights * 64
+    uint32_t w1;     // the two tap weights of window row 1
 };
+
+// cv2's fixed-point weight of one tap, doubled: column weight x row weight (0..32 each, 1/32 px)
+// x 64, so that sum(w * p) + 2^15 has the result in byte 2.  32 * 32 * 64 does not fit 16 bits;
+// it only occurs when that tap is the pixel's only non-zero one, and 65535 then gives the same
+// byte: (65535 p + 32768) >> 16 = p for p <= 255.
+__device__ __forceinline__ uint32_t tap_weight(int wc, int wr)
+{
+    return min((uint32_t)(wc * wr) * 64u, 65535u);
+}
 
 // One pixel out of its staged window: cv2's fixed-point bilinear, result [c0, c1, c2, 0].
 // f0 / g0 = window bytes 0..3 of row 0 / 1, f1 / g1 = window bytes 4.. (already byte-aligned).
+// Per row the channel pairs are gathered into [B0 B3 B1 B4] and [B2 B5 . .]; every channel is then
+// two chained dp2a (row 0, row 1) starting from the rounding constant -- no multiplies.
 __device__ __forceinline__ uint32_t lerp_aligned(const Pix &q, uint32_t f0, uint32_t f1, uint32_t g0,
                                                  uint32_t g1)
 {
-    // F = [B0 B1 B2 B3], G = [B1 B4 B2 B5]
-    const uint32_t fg = prmt(f0, f1, 0x5241u), gg = prmt(g0, g1, 0x5241u);
-    // horizontal pass: h[row][channel] = a0 * tap0 + a1 * tap1
-    const uint32_t h00 = __dp4a(f0, q.w03, 0u);
-    const uint32_t h01 = __dp2a_lo(q.w16, fg, 0u);
-    const uint32_t h02 = __dp2a_hi(q.w16, fg, 0u);
-    const uint32_t h10 = __dp4a(g0, q.w03, 0u);
-    const uint32_t h11 = __dp2a_lo(q.w16, gg, 0u);
-    const uint32_t h12 = __dp2a_hi(q.w16, gg, 0u);
-    // vertical pass, scaled by 64: byte 2 of t is (sum w*p + 2^14) >> 15
-    const uint32_t t0 = q.b1 * h10 + (q.b0 * h00 + 32768u);
-    const uint32_t t1 = q.b1 * h11 + (q.b0 * h01 + 32768u);
-    const uint32_t t2 = q.b1 * h12 + (q.b0 * h02 + 32768u);
+    const uint32_t xa = prmt(f0, f1, 0x4130u), ya = prmt(f0, f1, 0x0052u);
+    const uint32_t xb = prmt(g0, g1, 0x4130u), yb = prmt(g0, g1, 0x0052u);
+    const uint32_t t0 = __dp2a_lo(q.w1, xb, __dp2a_lo(q.w0, xa, 32768u));
+    const uint32_t t1 = __dp2a_hi(q.w1, xb, __dp2a_hi(q.w0, xa, 32768u));
+    const uint32_t t2 = __dp2a_lo(q.w1, yb, __dp2a_lo(q.w0, ya, 32768u));
+    // byte 2 of t is (sum w*p + 2^14) >> 15 in cv2's scale
     return prmt(prmt(t0, t1, 0x4462u), t2, 0x7610u);
 }
 
@@ -78,13 +81,11 @@ struct PxU8C3 {
         q.addr = A & ~3u;
         q.sh = 8 * (A & 3);
         if (LINEAR) {
-            q.w03 = wc0 | (wc1 << 24);
-            q.w16 = wc0 | (wc1 << 16);
-            q.b0 = wr0 * 64;
-            q.b1 = wr1 * 64;
+            q.w0 = tap_weight(wc0, wr0) | (tap_weight(wc1, wr0) << 16);
+            q.w1 = tap_weight(wc0, wr1) | (tap_weight(wc1, wr1) << 16);
         } else {
-            q.w03 = act ? 0x00ffffffu : 0u;
-            q.w16 = q.b0 = q.b1 = 0;
+            q.w0 = act ? 0x00ffffffu : 0u;
+            q.w1 = 0;
         }
         return q;
     }
@@ -115,7 +116,7 @@ struct PxU8C3 {
         if (LINEAR)  // byte-align the window of both rows, then interpolate
             return lerp_aligned(q, __funnelshift_r(w[0], w[1], q.sh), __funnelshift_r(w[1], w[2], q.sh),
                                 __funnelshift_r(w[3], w[4], q.sh), __funnelshift_r(w[4], w[5], q.sh));
-        return __funnelshift_r(w[0], w[1], q.sh) & q.w03;
+        return __funnelshift_r(w[0], w[1], q.sh) & q.w0;
     }
 
     // Lanes 4j..4j+2 write words 3j..3j+2 of a 96-byte segment (32 pixels).
