@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(256) composite_bev_kernel(const __grid_constan
     uint8_t *dst = p.out + ((long long)y * p.dst_w + x0) * 3 + (3 * j + r4) * 4;
 
     uint32_t B = p.bg_shared ? gather_pixel(tb, p.bg) : 0u;
-#pragma unroll 2
+#pragma unroll 4
     for (int f = f0; f < f1; ++f) {
         const long long fr = g.first + f;
         if (!p.bg_shared) B = gather_pixel(tb, p.bg + fr * p.bg_frame);
