@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256) resize_u8c3_kernel(const __grid_constant_
         const int s12 = __dp2a_lo(w16, prmt(fb, gb, 0x0052u), 0u);
         const uint32_t P = vpass(b0, b1, s00, s10) | (vpass(b0, b1, s01, s11) << 8) | (vpass(b0, b1, s02, s12) << 16);
         const uint32_t word = prmt(P, __shfl_down_sync(0xffffffffu, P, 1), sel_pack);
-        if (st_ok) st_stream(reinterpret_cast<uint32_t *>(dst + f * p.dst_frame), word);
+        if (st_ok) st_stream_free(reinterpret_cast<uint32_t *>(dst + f * p.dst_frame), word);
     }
 }
 

@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) warp_nearest_kernel(const __grid_constant
 // its 32 pixels into 24 words -- one coalesced 96-byte store per warp and frame.  This is the
 // kernel for strongly minifying maps (BrnoCompSpeed-sized BEVs of 1080p frames), where a tile's
 // source box is mostly untouched pixels and staging it would move more data than the gather.
-template <bool LINEAR>
+template <bool LINEAR, int kBatch>
 __global__ void __launch_bounds__(256) warp_u8c3_direct_kernel(const __grid_constant__ BevkWarpParams p)
 {
     const int lane = threadIdx.x, x0 = blockIdx.x * 32;
@@ -209,26 +209,47 @@ __global__ void __launch_bounds__(256) warp_u8c3_direct_kernel(const __grid_cons
     const uint8_t *src = (const uint8_t *)p.src;
     uint8_t *dst = (uint8_t *)p.dst + ((long long)y * p.dst_w + x0) * 3 + (3 * j + r4) * 4;
 
-#pragma unroll 2
-    for (int f = f0; f < f1; ++f) {
-        const long long fr = (long long)(g.first + f * g.stride);
-        const uint8_t *s = src + fr * p.src_frame_elems;
-        uint32_t P;
+    // The loop lives on loads in flight: the windows of kBatch frames are requested before the
+    // first one is interpolated (explicitly -- left to itself the compiler keeps one frame's worth).
+    constexpr int kWords = LINEAR ? 6 : 2;
+    auto load = [&](int f, uint32_t(&w)[kWords]) {
+        const uint8_t *s = src + (long long)(g.first + f * g.stride) * p.src_frame_elems;
         if (LINEAR) {
             const uint8_t *ra = s + q.addr, *rb = ra + row_bytes;
-            const uint32_t r0 = __ldg((const uint32_t *)ra), r1 = __ldg((const uint32_t *)(ra + 4));
-            const uint32_t r2 = __ldg((const uint32_t *)(s + off2));
-            const uint32_t s0 = __ldg((const uint32_t *)rb), s1 = __ldg((const uint32_t *)(rb + 4));
-            const uint32_t s2 = __ldg((const uint32_t *)(s + off2 + row_bytes));
-            P = lerp_aligned(q, __funnelshift_r(r0, r1, q.sh), __funnelshift_r(r1, r2, q.sh),
-                             __funnelshift_r(s0, s1, q.sh), __funnelshift_r(s1, s2, q.sh));
+            w[0] = __ldg((const uint32_t *)ra);
+            w[1] = __ldg((const uint32_t *)(ra + 4));
+            w[2] = __ldg((const uint32_t *)(s + off2));
+            w[3] = __ldg((const uint32_t *)rb);
+            w[4] = __ldg((const uint32_t *)(rb + 4));
+            w[5] = __ldg((const uint32_t *)(s + off2 + row_bytes));
         } else {
-            const uint32_t r0 = __ldg((const uint32_t *)(s + q.addr));
-            const uint32_t r1 = __ldg((const uint32_t *)(s + off2));
-            P = __funnelshift_r(r0, r1, q.sh) & q.w0;
+            w[0] = __ldg((const uint32_t *)(s + q.addr));
+            w[1] = __ldg((const uint32_t *)(s + off2));
         }
+    };
+    auto finish = [&](int f, const uint32_t(&w)[kWords]) {
+        uint32_t P;
+        if (LINEAR)
+            P = lerp_aligned(q, __funnelshift_r(w[0], w[1], q.sh), __funnelshift_r(w[1], w[2], q.sh),
+                             __funnelshift_r(w[3], w[4], q.sh), __funnelshift_r(w[4], w[5], q.sh));
+        else
+            P = __funnelshift_r(w[0], w[1], q.sh) & q.w0;
         const uint32_t word = prmt(P, __shfl_down_sync(0xffffffffu, P, 1), sel_pack);
-        if (st_ok) st_stream(reinterpret_cast<uint32_t *>(dst + fr * p.dst_frame_elems), word);
+        const long long fr = (long long)(g.first + f * g.stride);
+        if (st_ok) st_stream_free(reinterpret_cast<uint32_t *>(dst + fr * p.dst_frame_elems), word);
+    };
+    int f = f0;
+    for (; f + kBatch <= f1; f += kBatch) {
+        uint32_t w[kBatch][kWords];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) load(f + u, w[u]);
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) finish(f + u, w[u]);
+    }
+    for (; f < f1; ++f) {
+        uint32_t w[kWords];
+        load(f, w);
+        finish(f, w);
     }
 }
 
@@ -244,9 +265,9 @@ bool launch_u8c3_direct(const BevkWarpParams &p, int linear, cudaStream_t stream
     dim3 block(32, 8, 1);
     dim3 grid((p.dst_w + 31) / 32, (p.dst_h + 7) / 8, p.total_chunks);
     if (linear)
-        warp_u8c3_direct_kernel<true><<<grid, block, 0, stream>>>(p);
+        warp_u8c3_direct_kernel<true, 2><<<grid, block, 0, stream>>>(p);
     else
-        warp_u8c3_direct_kernel<false><<<grid, block, 0, stream>>>(p);
+        warp_u8c3_direct_kernel<false, 4><<<grid, block, 0, stream>>>(p);
     return true;
 }
 

@@ -13,6 +13,9 @@ __device__ __forceinline__ void st_stream(uint32_t *p, uint32_t v)
 {
     asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// The same streaming store as a compiler intrinsic: no memory clobber, so the gather kernels'
+// loads of the NEXT frame may be hoisted above it (their loops live on loads in flight).
+__device__ __forceinline__ void st_stream_free(uint32_t *p, uint32_t v) { __stcs(p, v); }
 
 // 2-tap window along one axis: first index (clamped into the image) and the weight each of the
 // two window positions receives.  Taps outside [0, n) contribute nothing (border value 0).
