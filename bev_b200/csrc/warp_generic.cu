@@ -212,19 +212,21 @@ __global__ void __launch_bounds__(256) warp_u8c3_direct_kernel(const __grid_cons
     // The loop lives on loads in flight: the windows of kBatch frames are requested before the
     // first one is interpolated (explicitly -- left to itself the compiler keeps one frame's worth).
     constexpr int kWords = LINEAR ? 6 : 2;
+    // 64-byte L2 fetches: this kernel serves the minifying maps, which use a fraction of each line
+    auto LD = [](const uint32_t *a) { return ldg_sparse(a); };
     auto load = [&](int f, uint32_t(&w)[kWords]) {
         const uint8_t *s = src + (long long)(g.first + f * g.stride) * p.src_frame_elems;
         if (LINEAR) {
             const uint8_t *ra = s + q.addr, *rb = ra + row_bytes;
-            w[0] = __ldg((const uint32_t *)ra);
-            w[1] = __ldg((const uint32_t *)(ra + 4));
-            w[2] = __ldg((const uint32_t *)(s + off2));
-            w[3] = __ldg((const uint32_t *)rb);
-            w[4] = __ldg((const uint32_t *)(rb + 4));
-            w[5] = __ldg((const uint32_t *)(s + off2 + row_bytes));
+            w[0] = LD((const uint32_t *)ra);
+            w[1] = LD((const uint32_t *)(ra + 4));
+            w[2] = LD((const uint32_t *)(s + off2));
+            w[3] = LD((const uint32_t *)rb);
+            w[4] = LD((const uint32_t *)(rb + 4));
+            w[5] = LD((const uint32_t *)(s + off2 + row_bytes));
         } else {
-            w[0] = __ldg((const uint32_t *)(s + q.addr));
-            w[1] = __ldg((const uint32_t *)(s + off2));
+            w[0] = LD((const uint32_t *)(s + q.addr));
+            w[1] = LD((const uint32_t *)(s + off2));
         }
     };
     auto finish = [&](int f, const uint32_t(&w)[kWords]) {

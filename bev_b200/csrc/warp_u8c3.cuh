@@ -17,6 +17,16 @@ __device__ __forceinline__ void st_stream(uint32_t *p, uint32_t v)
 // loads of the NEXT frame may be hoisted above it (their loops live on loads in flight).
 __device__ __forceinline__ void st_stream_free(uint32_t *p, uint32_t v) { __stcs(p, v); }
 
+// Read-only word load that asks L2 for a 64-byte fetch instead of the default 128 (measured on
+// B200 with a strided probe: a 4-byte ld.global.nc pulls the whole 128-byte line from DRAM, the
+// .L2::64B form half of it).  For gathers that use a fraction of every line -- minifying warps.
+__device__ __forceinline__ uint32_t ldg_sparse(const uint32_t *p)
+{
+    uint32_t v;
+    asm("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
 // 2-tap window along one axis: first index (clamped into the image) and the weight each of the
 // two window positions receives.  Taps outside [0, n) contribute nothing (border value 0).
 __device__ __forceinline__ void window(int s, int frac, int n, int &first, int &w0, int &w1)
