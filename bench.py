@@ -314,6 +314,9 @@ def ours(args, wl):
             torch.cuda.empty_cache()
             line["projection"] = projection_leg(dev, min(args.steps, 20), min(args.cpu_seconds, 5.0),
                                                 not args.no_cpu_baseline)
+        if world == 1 and not args.no_other_configs:
+            torch.cuda.empty_cache()
+            line["other_configs"] = other_configs(dev, min(args.steps, 10))
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -365,6 +368,67 @@ def projection_leg(dev, steps, cpu_seconds, with_cpu):
     return out
 
 
+def other_configs(dev, steps):
+    """Kernel-only numbers for the other BASELINE configs (inputs resident in HBM, CUDA events,
+    3 warm-up launches each): cfg 2 nearest, cfg 5 both directions in uint8 and float16, cfg 4
+    (8 cameras x 1000 frames, the homographies of tests/golden/cfg4_cams.json).  Reported inside
+    the one JSON line as `other_configs`; the headline stays cfg 2."""
+    import torch
+    from bev_b200 import _native, homo
+    peak, _ = measured_peak()
+    out = {}
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    for wl in ("cfg2_nearest", "cfg5_4k_to_bev2048_u8c3_x64", "cfg5_inv_bev2048_to_4k_u8c3_x64",
+               "cfg5_4k_to_bev2048_f16c3_x64", "cfg5_inv_bev2048_to_4k_f16c3_x64"):
+        n, ssize, dsize, ch, dtype, flags, hscale, inverse = WORKLOADS[wl]
+        H = np.linalg.inv(h_canon(hscale)) if inverse else h_canon(hscale)
+        es = 1 if dtype == "uint8" else 2
+        g = torch.Generator(device=dev).manual_seed(1234)
+        frames = torch.randint(0, 256, (n, ssize[1], ssize[0], ch), dtype=torch.uint8, device=dev, generator=g)
+        if dtype != "uint8":
+            frames = (frames.to(torch.float32) / 255.0).to(torch.float16)
+        dst = torch.empty((n, dsize[1], dsize[0], ch), dtype=frames.dtype, device=dev)
+        T, _, _ = _native.warp_touched_pixels(ssize, dsize, H, flags)
+        algo = (T + dsize[0] * dsize[1]) * ch * es * n
+        ms = timed(lambda: homo.warp_perspective(frames, H, dsize, dst=dst, flags=flags))
+        out[wl] = {"ms": ms, "Mpix_s": n * dsize[0] * dsize[1] / ms / 1e3, "roofline_frac": algo / (ms * 1e-3) / 1e9 / peak}
+        del frames, dst
+        torch.cuda.empty_cache()
+
+    cams = json.load(open(os.path.join(ROOT, "tests", "golden", "cfg4_cams.json")))
+    n = 1000
+    g = torch.Generator(device=dev).manual_seed(1234)
+    frames = torch.randint(0, 256, (n, 1080, 1920, 3), dtype=torch.uint8, device=dev, generator=g)
+    tot_ms, tot_px, tot_bytes = 0.0, 0, 0
+    for c in cams:
+        H = np.array(c["H_bev_img"])
+        dsize = (int(c["bspec"]["u_size"]), int(c["bspec"]["v_size"]))
+        dst = torch.empty((n, dsize[1], dsize[0], 3), dtype=torch.uint8, device=dev)
+        T, _, _ = _native.warp_touched_pixels((1920, 1080), dsize, H, 1)
+        tot_ms += timed(lambda: homo.warp_perspective(frames, H, dsize, dst=dst))
+        tot_px += n * dsize[0] * dsize[1]
+        tot_bytes += (T + dsize[0] * dsize[1]) * 3 * n
+        del dst
+    out["cfg4_8cams_x1000_1080p_to_brno_bevs"] = {
+        "ms": tot_ms, "Mpix_s": tot_px / tot_ms / 1e3, "roofline_frac": tot_bytes / (tot_ms * 1e-3) / 1e9 / peak,
+        "note": "8 launches (one per camera); DRAM traffic is at the 64-byte-granular floor (DESIGN.md 3.2)"}
+    del frames
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -378,6 +442,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling aid: skip the host-buffer leg")
     ap.add_argument("--no-projection", action="store_true", help="skip the rbox projection leg")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the kernel-only numbers of the other BASELINE configs")
     args = ap.parse_args()
 
     if args.impl == "reference":
