@@ -197,11 +197,42 @@ def iou_bench(n=8192, steps=10):
              100.0 * float((out > 0).float().mean())))
 
 
+def host_single(steps=200):
+    """The reference's own loop shape (vis_homo.py:85-89): ONE host frame per call, result back in
+    host memory -- bevk_warp_perspective_host on pinned numpy-backed buffers, against cv2 on the
+    same frame with all host threads."""
+    import time
+    import cv2
+    H = bench.h_canon(1)
+    dsize = (1024, 1024)
+    rng = np.random.default_rng(0)
+    frame = rng.integers(0, 256, (1080, 1920, 3), dtype=np.uint8)
+    h_src = torch.from_numpy(frame).pin_memory()
+    h_dst = torch.empty((1024, 1024, 3), dtype=torch.uint8).pin_memory()
+    for _ in range(5):
+        _native.warp_perspective_host(h_src[None], H, dsize, dst=h_dst[None])
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        _native.warp_perspective_host(h_src[None], H, dsize, dst=h_dst[None])
+    ours = (time.perf_counter() - t0) / steps
+    assert np.array_equal(h_dst.numpy(), cv2.warpPerspective(frame, H, dsize))
+    for _ in range(3):
+        cv2.warpPerspective(frame, H, dsize)
+    t0 = time.perf_counter()
+    for _ in range(50):
+        cv2.warpPerspective(frame, H, dsize)
+    ref = (time.perf_counter() - t0) / 50
+    print("one host frame per call: ours %.1f us (H2D + kernel + D2H, synchronous), cv2 %.1f us on %d threads"
+          % (ours * 1e6, ref * 1e6, cv2.getNumThreads()))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "cfg4":
         if len(sys.argv) > 3:
             _native.set_warp_path(sys.argv[3])
         cfg4(int(sys.argv[2]) if len(sys.argv) > 2 else 1000)
+    elif len(sys.argv) > 1 and sys.argv[1] == "host1":
+        host_single()
     elif len(sys.argv) > 1 and sys.argv[1] == "iou":
         iou_bench(int(sys.argv[2]) if len(sys.argv) > 2 else 8192)
     elif len(sys.argv) > 1 and sys.argv[1] == "resize":
