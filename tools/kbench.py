@@ -226,11 +226,44 @@ def host_single(steps=200):
           % (ours * 1e6, ref * 1e6, cv2.getNumThreads()))
 
 
+def cams_uniform(n_frames=256, steps=5):
+    """SURVEY 8d secondary variant of cfg 4: the eight BrnoCompSpeed-shaped cameras warped to a
+    uniform 1024^2 BEV (their own BEV rectangle stretched to it), n_frames 1080p frames each."""
+    import json
+    cams = json.load(open(os.path.join(ROOT, "tests", "golden", "cfg4_cams.json")))
+    peak, _ = bench.measured_peak()
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(1234)
+    frames = torch.randint(0, 256, (n_frames, 1080, 1920, 3), dtype=torch.uint8, device=dev, generator=g)
+    out = torch.empty((n_frames, 1024, 1024, 3), dtype=torch.uint8, device=dev)
+    for c in cams:
+        u, v = int(c["bspec"]["u_size"]), int(c["bspec"]["v_size"])
+        H = np.diag([1024.0 / u, 1024.0 / v, 1.0]) @ np.array(c["H_bev_img"])
+        T, _, _ = _native.warp_touched_pixels((1920, 1080), (1024, 1024), H, 1)
+        algo = (T + 1024 * 1024) * 3 * n_frames
+        for _ in range(2):
+            homo.warp_perspective(frames, H, (1024, 1024), dst=out)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            homo.warp_perspective(frames, H, (1024, 1024), dst=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        print("cam %s -> 1024^2 x%d: T %.0fk px, %.3f ms %.0f Mpix/s frac %.3f" % (
+            c["id"], n_frames, T / 1e3, ms, n_frames * 1024 * 1024 / ms / 1e3, algo / (ms * 1e-3) / 1e9 / peak))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "cfg4":
         if len(sys.argv) > 3:
             _native.set_warp_path(sys.argv[3])
         cfg4(int(sys.argv[2]) if len(sys.argv) > 2 else 1000)
+    elif len(sys.argv) > 1 and sys.argv[1] == "cams1024":
+        if len(sys.argv) > 2:
+            _native.set_warp_path(sys.argv[2])
+        cams_uniform()
     elif len(sys.argv) > 1 and sys.argv[1] == "host1":
         host_single()
     elif len(sys.argv) > 1 and sys.argv[1] == "iou":
