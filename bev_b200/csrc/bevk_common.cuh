@@ -128,12 +128,21 @@ struct BevkWarpParams {
     int n_groups;
     int total_chunks;
     float border[4];
+    // Split launches (staged kernel + direct-gather kernel over the tiles the first one could not
+    // stage): one byte per (group, staged tile), index = group * hard_tiles + tile_x * hard_ty +
+    // tile_y.  The staged kernel sets the byte and skips the tile; the direct kernel, when the
+    // pointer is set, only works on 32x8 blocks whose staged tile (hard_tw x hard_th pixels) is
+    // marked.  NULL: no split.
+    unsigned char *hard;
+    int hard_tw, hard_th, hard_ty, hard_tiles;
     BevkWarpGroup g[BEVK_MAX_GROUPS];
 };
 
 // kernels-side entry points implemented in the .cu files
 int bevk_launch_warp_generic(const BevkWarpParams &p, int channels, int dtype, int linear,
                              cudaStream_t stream);
+// fills frames_per_chunk, total_chunks and the groups' chunk0 for the direct-gather kernels
+int bevk_plan_generic_chunks(BevkWarpParams &p, int channels);
 // returns 1 if it launched, 0 if the shape does not qualify for the staged path (or, unless
 // `force`, is too small a batch to amortise its per-tile set-up), <0 on error
 int bevk_launch_warp_fast(const BevkWarpParams &p, int channels, int dtype, int linear, int force,

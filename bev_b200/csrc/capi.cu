@@ -240,26 +240,9 @@ int run_warp_device(const void *src, void *dst, const WarpArgs &a,
                 BEVK_FAIL(BEVK_E_ARG, "warp: shape does not qualify for the staged fast path");
         }
         if (!launched) {
-            // Frames per chunk: large enough to amortise the FP64 coordinate set-up, small enough
-            // that the grid still covers every SM with a few waves of blocks.
-            const long long tiles = (long long)((a.dst_w + 31) / 32) * ((a.dst_h + 7) / 8);
-            const long long want_blocks = (long long)bevk_sm_count() * 8 * 2;
-            int fpc = std::min(max_count, 64);
-            while (fpc > 1) {
-                long long blocks = 0;
-                for (int i = 0; i < ng; ++i) blocks += tiles * ((p.g[i].count + fpc - 1) / fpc);
-                if (blocks >= want_blocks) break;
-                fpc = (fpc + 1) / 2;
-            }
-            p.frames_per_chunk = fpc;
-            int z = 0;
-            for (int i = 0; i < ng; ++i) {
-                p.g[i].chunk0 = z;
-                z += (p.g[i].count + fpc - 1) / fpc;
-            }
-            p.total_chunks = z;
-            if (z > 65535) BEVK_FAIL(BEVK_E_ARG, "warp: too many frame chunks (%d) for one launch", z);
-            int rc = bevk_launch_warp_generic(p, a.channels, a.dtype, a.linear, stream);
+            int rc = bevk_plan_generic_chunks(p, a.channels);
+            if (rc) return rc;
+            rc = bevk_launch_warp_generic(p, a.channels, a.dtype, a.linear, stream);
             if (rc) return rc;
         }
     }

@@ -580,6 +580,9 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
             __syncthreads();  // every warp has read s_use and left the ring
             if (tid == 0) s_use[slog - 1] = use;
             continue;
+        } else if (p.hard) {
+            // split launch: leave the tile to the direct-gather kernel that follows on the stream
+            if (tid == 0) p.hard[gi * p.hard_tiles + tile_x * tiles_y + tile_y] = 1;
         } else {
             // bounding box too large for the ring (strong minification) or too wide / tall for the
             // tensor-map menu: the same arithmetic on aligned 32-bit loads straight from global
@@ -641,6 +644,10 @@ std::mutex g_map_mutex;
 EncodeTiledFn g_encode = nullptr;
 
 constexpr int kCounterSlots = 1024;
+unsigned char *g_flags = nullptr;  // split launches: ring of flag slices
+int g_flags_dev = -1;
+unsigned g_flag_next = 0;
+constexpr int kFlagSlices = 16, kFlagSliceBytes = 256 * 1024;
 int *g_counters = nullptr;
 int g_counters_dev = -1;
 unsigned g_counter_next = 0;
@@ -835,9 +842,14 @@ struct ModeKey {
 struct ModeEntry {
     ModeKey key;
     int segs;  // 4, 2, 1, or 0: leave it to the direct-gather kernel
+    int best;  // the shape with the fewest unstaged tiles (what a forced launch uses)
+    bool split;
     unsigned long long stamp = 0;
     bool valid = false;
 };
+// Above this fraction of unstaged tiles the whole launch goes to the direct-gather kernel; between
+// kNegligible and this the launch is split (staged kernel + direct kernel over the marked tiles).
+constexpr double kMaxSplit = 0.35;
 constexpr int kModeCacheSize = 8;
 ModeEntry g_mode_cache[kModeCacheSize];
 unsigned long long g_mode_stamp = 0;
@@ -845,10 +857,11 @@ unsigned long long g_mode_stamp = 0;
 // Largest tile shape whose boxes all stage; 0 if even the best shape leaves more than
 // kMaxUnstaged of the tiles to the in-kernel fallback (strong minification: the boxes are mostly
 // untouched pixels, the direct-gather kernel moves less data).
-int pick_tile_shape(const BevkWarpParams &p, int linear, int bpp, int ring_bytes, bool force)
+// *split is set when the chosen shape still leaves a noticeable fraction of the tiles unstaged:
+// those tiles are cheaper in a second, direct-gather launch than in the staged kernel's fallback.
+int pick_tile_shape(const BevkWarpParams &p, int linear, int bpp, int ring_bytes, bool force, bool *split)
 {
     // nearest reads one tap per pixel, so its in-kernel fallback costs little: keep wide tiles
-    constexpr double kMaxUnstaged = 0.05;
     const double kNegligible = linear ? 0.002 : 0.05;
     ModeKey key;
     memset(&key, 0, sizeof(key));
@@ -866,7 +879,8 @@ int pick_tile_shape(const BevkWarpParams &p, int linear, int bpp, int ring_bytes
         ModeEntry &e = g_mode_cache[i];
         if (e.valid && memcmp(&e.key, &key, sizeof(key)) == 0) {
             e.stamp = ++g_mode_stamp;
-            return (e.segs == 0 && force) ? 1 : e.segs;
+            *split = e.split && e.segs != 0;
+            return (e.segs == 0 && force) ? e.best : e.segs;
         }
         if (e.stamp < victim->stamp) victim = &e;
     }
@@ -884,12 +898,16 @@ int pick_tile_shape(const BevkWarpParams &p, int linear, int bpp, int ring_bytes
         }
         if (f <= kNegligible) break;
     }
-    const int segs = best_frac <= kMaxUnstaged ? best : 0;
+    const int segs = best_frac <= kMaxSplit ? best : 0;
     victim->key = key;
     victim->segs = segs;
+    victim->best = best ? best : 1;
+    // up to ~2 % the in-kernel fallback is as fast as a second launch (measured on the cfg-4 cameras)
+    victim->split = best_frac > (kNegligible > 0.02 ? kNegligible : 0.02);
     victim->stamp = ++g_mode_stamp;
     victim->valid = true;
-    return (segs == 0 && force) ? (best ? best : 1) : segs;
+    *split = victim->split && segs != 0;
+    return (segs == 0 && force) ? victim->best : segs;
 }
 
 }  // namespace
@@ -930,7 +948,8 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
         int rc = fmt ? configure_any<PxF16C3>(linear, 4, cfg0) : configure_any<PxU8C3>(linear, 4, cfg0);
         if (rc) return rc;
     }
-    const int segs = pick_tile_shape(p, linear, bpp, cfg0.ring_bytes, force != 0);
+    bool split = false;
+    const int segs = pick_tile_shape(p, linear, bpp, cfg0.ring_bytes, force != 0, &split);
     if (segs == 0) return 0;
     KernelConfig &cfg = g_cfg[fmt][linear ? 1 : 0][segs_index(segs)];
     if (!cfg.ready) {
@@ -988,6 +1007,27 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
     }
     if (counter) BEVK_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));
 
+    // split launch: one byte per (group, tile), a zeroed slice of a ring of flag buffers
+    const long long n_flags = n_tiles * p.n_groups;
+    split = split && fmt == 0 && n_flags <= kFlagSliceBytes;
+    if (split) {
+        std::lock_guard<std::mutex> lock(g_map_mutex);
+        int dev = 0;
+        BEVK_CUDA(cudaGetDevice(&dev));
+        if (!g_flags || g_flags_dev != dev) {
+            if (g_flags) cudaFree(g_flags);
+            g_flags = nullptr;
+            BEVK_CUDA(cudaMalloc(&g_flags, (size_t)kFlagSlices * kFlagSliceBytes));
+            g_flags_dev = dev;
+        }
+        p.hard = g_flags + (size_t)(g_flag_next++ % kFlagSlices) * kFlagSliceBytes;
+        p.hard_tw = tile_w(segs);
+        p.hard_th = tile_h(segs);
+        p.hard_ty = tiles_y;
+        p.hard_tiles = (int)n_tiles;
+        BEVK_CUDA(cudaMemsetAsync(p.hard, 0, (size_t)n_flags, stream));
+    }
+
     const int smem = cfg.ring_bytes + kBarBytes + kTailSlack;
     if (fmt)
         launch_any<PxF16C3>(linear, segs, grid, smem, stream, p, maps, plan, tiles_x, tiles_y, (int)items,
@@ -996,5 +1036,12 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
         launch_any<PxU8C3>(linear, segs, grid, smem, stream, p, maps, plan, tiles_x, tiles_y, (int)items,
                            cfg.ring_bytes, counter);
     BEVK_CUDA(cudaGetLastError());
+    if (split) {
+        // the tiles the staged kernel marked, through the direct-gather kernel (same stream)
+        int rc2 = bevk_plan_generic_chunks(p, channels);
+        if (rc2) return rc2;
+        rc2 = bevk_launch_warp_generic(p, channels, dtype, linear, stream);
+        if (rc2) return rc2;
+    }
     return 1;
 }

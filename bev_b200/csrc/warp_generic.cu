@@ -177,6 +177,9 @@ __global__ void __launch_bounds__(256) warp_u8c3_direct_kernel(const __grid_cons
     if (y >= p.dst_h) return;  // a warp is one dst row segment: uniform exit, shuffles stay legal
     int gi;
     const BevkWarpGroup &g = find_group(p, blockIdx.z, gi);
+    // second half of a split launch: only the tiles the staged kernel marked (block-uniform)
+    if (p.hard && !p.hard[gi * p.hard_tiles + (x0 / p.hard_tw) * p.hard_ty + (int)(blockIdx.y * 8) / p.hard_th])
+        return;
     const int c_local = blockIdx.z - g.chunk0;
     const int f0 = c_local * p.frames_per_chunk;
     const int f1 = min(f0 + p.frames_per_chunk, g.count);
@@ -299,6 +302,34 @@ int launch_t(const BevkWarpParams &p, int channels, int linear, cudaStream_t str
 }
 
 }  // namespace
+
+int bevk_plan_generic_chunks(BevkWarpParams &p, int channels)
+{
+    (void)channels;
+    // Frames per chunk: large enough to amortise the FP64 coordinate set-up, small enough that the
+    // grid still covers every SM with a few waves of blocks.
+    const long long tiles = (long long)((p.dst_w + 31) / 32) * ((p.dst_h + 7) / 8);
+    const long long want_blocks = (long long)bevk_sm_count() * 8 * 2;
+    int max_count = 0;
+    for (int i = 0; i < p.n_groups; ++i) max_count = max_count > p.g[i].count ? max_count : p.g[i].count;
+    int fpc = max_count < 64 ? max_count : 64;
+    while (fpc > 1) {
+        long long blocks = 0;
+        for (int i = 0; i < p.n_groups; ++i) blocks += tiles * ((p.g[i].count + fpc - 1) / fpc);
+        if (blocks >= want_blocks) break;
+        fpc = (fpc + 1) / 2;
+    }
+    fpc = fpc < 1 ? 1 : fpc;
+    p.frames_per_chunk = fpc;
+    int z = 0;
+    for (int i = 0; i < p.n_groups; ++i) {
+        p.g[i].chunk0 = z;
+        z += (p.g[i].count + fpc - 1) / fpc;
+    }
+    p.total_chunks = z;
+    if (z > 65535) BEVK_FAIL(BEVK_E_ARG, "warp: too many frame chunks (%d) for one launch", z);
+    return BEVK_OK;
+}
 
 int bevk_launch_warp_generic(const BevkWarpParams &p, int channels, int dtype, int linear,
                              cudaStream_t stream)
