@@ -227,11 +227,7 @@ int run_warp_device(const void *src, void *dst, const WarpArgs &a,
     for (size_t g0 = 0; g0 < groups.size(); g0 += BEVK_MAX_GROUPS) {
         const int ng = (int)std::min<size_t>(BEVK_MAX_GROUPS, groups.size() - g0);
         p.n_groups = ng;
-        int max_count = 0;
-        for (int i = 0; i < ng; ++i) {
-            p.g[i] = groups[g0 + i];
-            max_count = std::max(max_count, p.g[i].count);
-        }
+        for (int i = 0; i < ng; ++i) p.g[i] = groups[g0 + i];
         int launched = 0;
         if (g_warp_path != 1) {
             launched = bevk_launch_warp_fast(p, a.channels, a.dtype, a.linear, g_warp_path == 2, stream);
