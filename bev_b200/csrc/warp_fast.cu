@@ -1009,7 +1009,7 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
 
     // split launch: one byte per (group, tile), a zeroed slice of a ring of flag buffers
     const long long n_flags = n_tiles * p.n_groups;
-    split = split && fmt == 0 && n_flags <= kFlagSliceBytes;
+    split = split && n_flags <= kFlagSliceBytes;
     if (split) {
         std::lock_guard<std::mutex> lock(g_map_mutex);
         int dev = 0;

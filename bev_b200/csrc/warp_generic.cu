@@ -31,6 +31,14 @@ __device__ __forceinline__ const BevkWarpGroup &find_group(const BevkWarpParams 
     return p.g[gi];
 }
 
+// Second half of a split launch (BevkWarpParams::hard): is this 32x8 block's staged tile unmarked,
+// i.e. already written by the staged kernel?  Block-uniform.
+__device__ __forceinline__ bool skip_block(const BevkWarpParams &p, int gi)
+{
+    return p.hard && !p.hard[gi * p.hard_tiles + (int)(blockIdx.x * 32) / p.hard_tw * p.hard_ty +
+                             (int)(blockIdx.y * 8) / p.hard_th];
+}
+
 __device__ __forceinline__ uint8_t border_u8(float b)
 {
     // cv2: saturate_cast<uchar>(borderValue[c])
@@ -47,6 +55,7 @@ __global__ void __launch_bounds__(256) warp_linear_kernel(const __grid_constant_
     if (x >= p.dst_w || y >= p.dst_h) return;
     int gi;
     const BevkWarpGroup &g = find_group(p, blockIdx.z, gi);
+    if (skip_block(p, gi)) return;
     const int c_local = blockIdx.z - g.chunk0;
     const int f0 = c_local * p.frames_per_chunk;
     const int f1 = min(f0 + p.frames_per_chunk, g.count);
@@ -130,6 +139,7 @@ __global__ void __launch_bounds__(256) warp_nearest_kernel(const __grid_constant
     if (x >= p.dst_w || y >= p.dst_h) return;
     int gi;
     const BevkWarpGroup &g = find_group(p, blockIdx.z, gi);
+    if (skip_block(p, gi)) return;
     const int c_local = blockIdx.z - g.chunk0;
     const int f0 = c_local * p.frames_per_chunk;
     const int f1 = min(f0 + p.frames_per_chunk, g.count);
@@ -177,9 +187,7 @@ __global__ void __launch_bounds__(256) warp_u8c3_direct_kernel(const __grid_cons
     if (y >= p.dst_h) return;  // a warp is one dst row segment: uniform exit, shuffles stay legal
     int gi;
     const BevkWarpGroup &g = find_group(p, blockIdx.z, gi);
-    // second half of a split launch: only the tiles the staged kernel marked (block-uniform)
-    if (p.hard && !p.hard[gi * p.hard_tiles + (x0 / p.hard_tw) * p.hard_ty + (int)(blockIdx.y * 8) / p.hard_th])
-        return;
+    if (skip_block(p, gi)) return;  // split launch: only the tiles the staged kernel marked
     const int c_local = blockIdx.z - g.chunk0;
     const int f0 = c_local * p.frames_per_chunk;
     const int f1 = min(f0 + p.frames_per_chunk, g.count);

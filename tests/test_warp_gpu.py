@@ -120,6 +120,12 @@ def test_split_launch_on_camera_homographies(path):
         out = gpu_warp(frames, H, (1024, 1024), flags)
         for i in (0, 4):
             assert util.bits_equal(out[i], wo.warp_perspective(frames[i], H, (1024, 1024), flags)), (k, i)
+    # float16 frames take the same split (staged float16 policy + the generic float16 kernel)
+    f16 = np.stack([util.seeded_frame(950 + i, 1080, 1920, 3, "float16") for i in range(4)])
+    c = cams[1]
+    H = np.diag([1024.0 / c["bspec"]["u_size"], 1024.0 / c["bspec"]["v_size"], 1.0]) @ np.array(c["H_bev_img"])
+    out = gpu_warp(f16, H, (1024, 1024), 1)
+    assert util.bits_equal(out[3], wo.warp_perspective(f16[3], H, (1024, 1024), 1))
 
 
 def test_round_trip_img_bev_img(path):
