@@ -606,15 +606,16 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
 #pragma unroll 1
             for (int i = 0; i < n_frames; ++i, d += d_step, s += s_step) {
                 typename PX::Out P[4];
+                // all window words of the frame are requested before the first is used: this loop
+                // lives on loads in flight
+                uint32_t w[4][8];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    uint32_t w[8];
-                    // "addresses" are byte offsets inside the frame here
+                for (int k = 0; k < 4; ++k)  // "addresses" are byte offsets inside the frame here
                     PX::template load<LINEAR>(px[k], px[k].addr, px[k].addr + src_row_bytes, last[k],
-                                              last[k] + src_row_bytes, w,
-                                              [s](uint32_t off) { return __ldg((const uint32_t *)(s + off)); });
-                    P[k] = PX::template math<LINEAR>(px[k], w);
-                }
+                                              last[k] + src_row_bytes, w[k],
+                                              [s](uint32_t off) { return ldg_sparse((const uint32_t *)(s + off)); });
+#pragma unroll
+                for (int k = 0; k < 4; ++k) P[k] = PX::template math<LINEAR>(px[k], w[k]);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     PX::store(d + PX::kSegBytes * (k % SEGS) + (k / SEGS) * row_bytes, P[k], seg_ok[k], st, lane);
@@ -1009,7 +1010,7 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
 
     // split launch: one byte per (group, tile), a zeroed slice of a ring of flag buffers
     const long long n_flags = n_tiles * p.n_groups;
-    split = split && n_flags <= kFlagSliceBytes;
+    split = split && n_flags <= kFlagSliceBytes && !getenv("BEVK_NO_SPLIT");  // env: tuning aid
     if (split) {
         std::lock_guard<std::mutex> lock(g_map_mutex);
         int dev = 0;
