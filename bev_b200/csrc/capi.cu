@@ -303,13 +303,15 @@ void referenced_rows_union(const std::vector<double> &maps, int n_mats, const Wa
     }
 }
 
-// grow-only device workspace for the host-buffer entry point
+// grow-only device workspace for the host-buffer entry point: kHostSlots chunks in flight, each
+// with its own stream and device buffers
+constexpr int kHostSlots = 3;
 struct HostWorkspace {
     std::mutex mu;
-    void *d_src[2] = {nullptr, nullptr};
-    void *d_dst[2] = {nullptr, nullptr};
+    void *d_src[kHostSlots] = {};
+    void *d_dst[kHostSlots] = {};
     size_t src_cap = 0, dst_cap = 0;
-    cudaStream_t stream[2] = {nullptr, nullptr};
+    cudaStream_t stream[kHostSlots] = {};
     int device = -1;
 };
 HostWorkspace g_ws;
@@ -386,7 +388,7 @@ int bevk_warp_perspective_host(const void *src, void *dst, int n_frames, int src
     int dev = 0;
     BEVK_CUDA(cudaGetDevice(&dev));
     if (g_ws.device != dev) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kHostSlots; ++i) {
             if (g_ws.d_src[i]) cudaFree(g_ws.d_src[i]);
             if (g_ws.d_dst[i]) cudaFree(g_ws.d_dst[i]);
             g_ws.d_src[i] = g_ws.d_dst[i] = nullptr;
@@ -397,7 +399,7 @@ int bevk_warp_perspective_host(const void *src, void *dst, int n_frames, int src
         g_ws.device = dev;
     }
     if (g_ws.src_cap < src_frame_bytes * chunk) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kHostSlots; ++i) {
             if (g_ws.d_src[i]) cudaFree(g_ws.d_src[i]);
             g_ws.d_src[i] = nullptr;
             BEVK_CUDA(cudaMalloc(&g_ws.d_src[i], src_frame_bytes * chunk));
@@ -405,7 +407,7 @@ int bevk_warp_perspective_host(const void *src, void *dst, int n_frames, int src
         g_ws.src_cap = src_frame_bytes * chunk;
     }
     if (g_ws.dst_cap < dst_frame_bytes * chunk) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kHostSlots; ++i) {
             if (g_ws.d_dst[i]) cudaFree(g_ws.d_dst[i]);
             g_ws.d_dst[i] = nullptr;
             BEVK_CUDA(cudaMalloc(&g_ws.d_dst[i], dst_frame_bytes * chunk));
@@ -414,7 +416,7 @@ int bevk_warp_perspective_host(const void *src, void *dst, int n_frames, int src
     }
 
     int slot = 0;
-    for (int f0 = 0; f0 < n_frames; f0 += chunk, slot ^= 1) {
+    for (int f0 = 0; f0 < n_frames; f0 += chunk, slot = (slot + 1) % kHostSlots) {
         const int nf = std::min(chunk, n_frames - f0);
         cudaStream_t st = g_ws.stream[slot];
         // frames are "rows" of a 2-D copy: pitch = whole frame, width = the referenced row band
@@ -446,8 +448,7 @@ int bevk_warp_perspective_host(const void *src, void *dst, int n_frames, int src
         BEVK_CUDA(cudaMemcpyAsync((char *)dst + (size_t)f0 * dst_frame_bytes, g_ws.d_dst[slot],
                                   dst_frame_bytes * nf, cudaMemcpyDeviceToHost, st));
     }
-    BEVK_CUDA(cudaStreamSynchronize(g_ws.stream[0]));
-    BEVK_CUDA(cudaStreamSynchronize(g_ws.stream[1]));
+    for (int i = 0; i < kHostSlots; ++i) BEVK_CUDA(cudaStreamSynchronize(g_ws.stream[i]));
     return BEVK_OK;
 }
 
