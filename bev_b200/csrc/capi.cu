@@ -379,7 +379,7 @@ int bevk_warp_perspective_host(const void *src, void *dst, int n_frames, int src
     const size_t dst_frame_bytes = (size_t)a.dst_w * a.dst_h * a.channels * a.elem_size;
     const size_t up_bytes = row_bytes * (size_t)(r1 - r0 + 1);
 
-    // chunk so that copies and kernels of neighbouring chunks overlap (two streams, two buffers)
+    // chunk so that copies and kernels of neighbouring chunks overlap (kHostSlots streams and buffers)
     int chunk = (int)std::max<size_t>(1, (size_t)(64u << 20) / std::max(src_frame_bytes, dst_frame_bytes));
     chunk = std::min(chunk, std::max(1, (n_frames + 3) / 4));
     chunk = std::min(chunk, n_frames);
