@@ -1,38 +1,43 @@
-// warp_fast.cu -- staged perspective warp for uint8 x 3 channels (the BASELINE hot path:
+// warp_fast.cu -- staged perspective warp for 3-channel frames (the BASELINE hot path:
 // cv2.warpPerspective on BGR video frames, reference vis_homo.py:85-91), sm_100a.
 //
-// Work item = (homography group, 128x8 dst tile, chunk of frames).  A CTA of 8 warps owns one
-// item at a time; warp w owns tile row w, every thread owns 4 dst pixels of that row
-// (x = lane + 32k):
+// The kernel is written against a pixel-format policy PX (warp_u8c3.cuh: uint8 x 3,
+// warp_f16c3.cuh: float16 x 3) that owns the per-pixel registers, the window loads, the
+// interpolation and the store packing.
 //
-//   1. set-up, once per item: the exact FP64 coordinate pipeline of cv2 (bevk_map_pixel) gives
+// Work item = (chunk of frames, homography group, dst tile).  A persistent CTA of 8 warps pulls
+// items from a shared counter; a tile is 1024 dst pixels, 4 per thread, as 128x8, 64x16 or 32x32
+// (picked per launch on the host, pick_tile_shape):
+//
+//   1. set-up, once per item: the exact FP64 coordinate pipeline of cv2 (bevk_map_pixel_xb) gives
 //      each pixel its 2x2 source window, and frame-invariant registers are derived from it -- the
-//      shared-memory offset of the window, a funnel-shift amount that byte-aligns it and the
-//      8-bit interpolation weights already laid out as dp4a / dp2a operands.  Out-of-image taps
-//      get weight 0 and a clamped address, so the frame loop has no border branches.  A block
-//      reduction yields the tile's source bounding box.
+//      shared-memory offset of the window, a funnel-shift amount that byte-aligns it and the tap
+//      weights laid out as the policy's operands.  Out-of-image taps get weight 0 and a clamped
+//      address, so the frame loop has no border branches.  A block reduction yields the tile's
+//      source bounding box.
 //   2. frame loop: the bounding box of the next frames is fetched by the TMA unit as 2-D tensor
 //      boxes (cp.async.bulk.tensor.2d, at most 3 requests per frame and tile, completion on an
-//      mbarrier) into a 2- or 4-deep shared-memory ring while the warps interpolate the current
-//      frame out of shared memory.  One elected thread issues the copies; full[] / empty[]
-//      mbarriers are the only synchronisation in the loop.  The box shape is picked per tile from
-//      a menu of tensor maps over the source batch viewed as a [frames*rows][row_bytes/4] uint32
-//      matrix (widths 64..1024 B, heights 1..64 rows).  A first version issued one
-//      cp.async.bulk per source row: the TMA unit retired only one such ~300-byte request per
-//      ~70 cycles per SM, which capped the kernel at 33 % of the HBM roofline
-//      (profiles/r01_fast_v1_*).
-//      Interpolation is integer only and spread over both integer pipes: funnel shifts + PRMT
-//      (ALU pipe) align the window, dp4a / dp2a (FMA pipe) do the horizontal pass, IMAD with
-//      weights pre-scaled by 64 does the vertical pass so that the result lands in byte 2.  This
-//      reproduces cv2's (sum w*p + 2^14) >> 15 bit for bit (the two passes are an exact integer
-//      re-association of the same sum).
-//   3. stores: 4 lanes' pixels (12 B) are packed into 3 words with one shuffle + PRMT and
-//      written as fully coalesced 96 B segments, 384 contiguous bytes per warp and frame.
+//      mbarrier) into a 2-, 4- or 8-deep shared-memory ring of up to 4 frames per stage while the
+//      warps interpolate the current frames out of shared memory.  The producer role rotates over
+//      the warps (one elected lane); full[] / empty[] mbarriers are the only synchronisation in
+//      the loop.  The box shape is picked per tile from a menu of 224 tensor maps over the source
+//      batch viewed as a [frames*rows][row_bytes/4] uint32 (or /8 uint64) matrix: widths
+//      64..2048 B, heights 1..32 rows.  A first version issued one cp.async.bulk per source row:
+//      the TMA unit retired only one such ~300-byte request per ~70 cycles per SM, which capped
+//      the kernel at 33 % of the HBM roofline (profiles/r01_fast_v1_*).
+//   3. stores: the policy packs the lanes' pixels into words (one shuffle + PRMT for uint8) and
+//      writes fully coalesced row segments with streaming stores.
+//
+// Tiles whose box does not stage (too wide / tall for the menu, larger than half the ring): a few
+// of them fall back, inside the kernel, to aligned 32-bit global loads with the same arithmetic;
+// when the host predicts 2-35 % of the tiles the launch is SPLIT -- the kernel only marks them in
+// BevkWarpParams::hard and the direct-gather kernel (warp_generic.cu) follows on the stream over
+// the marked tiles; above that the whole launch goes to the direct-gather kernel.
 //
 // HBM traffic per frame is the touched source footprint (bounding boxes overlap by a row /
 // column and are re-served by L2: tiles are walked column-major so that neighbours run
-// concurrently and near-/far-field tiles mix) plus the output, i.e. the algorithmic bytes of
-// SURVEY.md 8d.
+// concurrently and near-/far-field tiles mix) plus the output, i.e. about 1.1x the algorithmic
+// bytes of SURVEY.md 8d.  The binding resource is the shared-memory data pipe.
 #include "bevk_common.cuh"
 #include "warp_u8c3.cuh"
 #include "warp_f16c3.cuh"
@@ -362,8 +367,6 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
     const long long src_frame_bytes = (long long)src_row_bytes * p.src_h;
     const long long dst_frame_bytes = (long long)p.dst_w * p.dst_h * kBpp;
 
-    // Items are (chunk, group, tile) with the chunk index slowest: long chunks first.  The first
-    // gridDim.x items are taken by block index, the rest are pulled from *next_item.
     // Items are (chunk, group, tile) with the chunk index slowest: long chunks first.  The first
     // gridDim.x items are taken by block index, the rest are pulled from *next_item.  Thread 0
     // decodes an item (integer divisions, parameter reads) one item ahead of its use.
