@@ -11,9 +11,12 @@
 // float64 numpy path near the horizon, where the reference's own float32 torch path is 2.3e-4 off
 // (SURVEY.md 0.5 / 8c).
 //
-// Layout: rows of 5 floats (20 B) are not 16 B aligned, so a block stages 256 rows through shared
-// memory with fully coalesced 4 B accesses on both sides; the row pitch in shared memory is odd
-// (W | 1 words) so the per-row reads are bank-conflict free.
+// Layout: rows of 5 floats (20 B) are not 16 B aligned, but a block of 256 rows is one contiguous,
+// 16-byte-aligned run: rows_bulk_kernel moves it with ONE cp.async.bulk into a shared-memory ring
+// (mbarrier completion) and writes the 256 result rows back with one bulk store; threads only
+// touch shared memory.  Unaligned buffers, float64 tensors and the tail of fewer than 256 rows go
+// through rows_kernel, which stages the rows with coalesced 4 B accesses and an odd row pitch in
+// shared memory (W | 1 words) so that the per-row reads are bank-conflict free.
 #include "bevk_common.cuh"
 
 namespace {
