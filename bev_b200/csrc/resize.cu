@@ -23,6 +23,15 @@
 
 namespace {
 
+// word load with a 256-byte L2 prefetch hint: the resize reads (nearly) every byte of the rows it
+// touches, so the neighbouring lines are wanted anyway (3 % faster than the plain read-only load)
+__device__ __forceinline__ uint32_t ldg_dense(const uint32_t *p)
+{
+    uint32_t v;
+    asm("ld.global.nc.L2::256B.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
 constexpr int kCoefScale = 2048;  // INTER_RESIZE_COEF_SCALE
 
 struct ResizeParams {
@@ -118,10 +127,10 @@ __global__ void __launch_bounds__(256) resize_u8c3_kernel(const __grid_constant_
     for (int f = f0; f < f1; ++f) {
         const uint8_t *s = p.src + f * p.src_frame;
         const uint8_t *pa = s + ra, *pb = s + rb;
-        const uint32_t u0 = __ldg((const uint32_t *)(pa + addr)), u1 = __ldg((const uint32_t *)(pa + addr + 4));
-        const uint32_t u2 = __ldg((const uint32_t *)(pa + off2));
-        const uint32_t v0 = __ldg((const uint32_t *)(pb + addr)), v1 = __ldg((const uint32_t *)(pb + addr + 4));
-        const uint32_t v2 = __ldg((const uint32_t *)(pb + off2));
+        const uint32_t u0 = ldg_dense((const uint32_t *)(pa + addr)), u1 = ldg_dense((const uint32_t *)(pa + addr + 4));
+        const uint32_t u2 = ldg_dense((const uint32_t *)(pa + off2));
+        const uint32_t v0 = ldg_dense((const uint32_t *)(pb + addr)), v1 = ldg_dense((const uint32_t *)(pb + addr + 4));
+        const uint32_t v2 = ldg_dense((const uint32_t *)(pb + off2));
         // byte-aligned windows: f = [B0 B1 B2 B3], g = [B4 B5 . .] of each row
         const uint32_t fa = __funnelshift_r(u0, u1, sh), ga = __funnelshift_r(u1, u2, sh);
         const uint32_t fb = __funnelshift_r(v0, v1, sh), gb = __funnelshift_r(v1, v2, sh);
