@@ -188,6 +188,8 @@ extern "C" int bevk_resize(const void *src, void *dst, int n_frames, int src_h, 
     const long long want_blocks = (long long)bevk_sm_count() * 8 * 2;
     int fpc = n_frames < 64 ? n_frames : 64;
     while (fpc > 1 && tiles * ((n_frames + fpc - 1) / fpc) < want_blocks) fpc = (fpc + 1) / 2;
+    // ~12 waves of blocks while a chunk keeps 8 frames: few long blocks leave a costly last wave
+    while (fpc >= 16 && tiles * ((n_frames + fpc - 1) / fpc) < 6 * want_blocks) fpc = (fpc + 1) / 2;
     p.frames_per_chunk = fpc;
     const int z = (n_frames + fpc - 1) / fpc;
     if (z > 65535) BEVK_FAIL(BEVK_E_ARG, "resize: too many frame chunks (%d) for one launch", z);
