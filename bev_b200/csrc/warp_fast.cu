@@ -976,14 +976,14 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
 
     // Frame chunks.  Every (tile, chunk) item pays one FP64 set-up, so chunks should be long; the
     // CTAs pull items from a shared counter, so the LAST items should be short.  With enough
-    // frames the chunk lengths therefore decay (5/16, 4/16, 3/16, 5/32, 3/32 of the frames);
+    // frames the chunk lengths therefore decay (5/16, 4/16, 3/16, 1/8, then ever smaller);
     // short batches get fewer, equal chunks, just enough for ~3 items per CTA.
     ChunkPlan plan;
     memset(&plan, 0, sizeof(plan));
     const long long tile_groups = n_tiles * p.n_groups;
     if (max_count >= 128 && tile_groups * 5 >= 2LL * ctas) {
-        static const uint32_t cum[6] = {0, 20480, 36864, 49152, 59392, 65536};
-        plan.n_chunks = 5;
+        static const uint32_t cum[8] = {0, 20480, 36864, 49152, 57344, 61952, 64512, 65536};
+        plan.n_chunks = 7;
         memcpy(plan.cum, cum, sizeof(cum));
     } else {
         int k = (int)((3LL * ctas + tile_groups - 1) / tile_groups);
