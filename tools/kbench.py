@@ -255,6 +255,35 @@ def cams_uniform(n_frames=256, steps=5):
             c["id"], n_frames, T / 1e3, ms, n_frames * 1024 * 1024 / ms / 1e3, algo / (ms * 1e-3) / 1e9 / peak))
 
 
+def cfg1_cold_warm(steps=50):
+    """BASELINE configs[0]: one 1080p frame -> 1024^2, per-call device time with the frame warm in
+    L2 (back-to-back calls) and cold (a 512 MB buffer is rewritten between calls)."""
+    dev = torch.device("cuda", 0)
+    H = bench.h_canon(1)
+    g = torch.Generator(device=dev).manual_seed(1234)
+    frame = torch.randint(0, 256, (1, 1080, 1920, 3), dtype=torch.uint8, device=dev, generator=g)
+    out = torch.empty((1, 1024, 1024, 3), dtype=torch.uint8, device=dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(5):
+        homo.warp_perspective(frame, H, (1024, 1024), dst=out)
+    torch.cuda.synchronize()
+    res = {}
+    for mode in ("warm", "cold"):
+        ev = []
+        for _ in range(steps):  # everything is queued; only the warp calls are bracketed by events
+            if mode == "cold":
+                flush.fill_(1)
+            torch.cuda._sleep(200000)  # ~100 us of device idle spin: the host runs ahead of the queue
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            homo.warp_perspective(frame, H, (1024, 1024), dst=out)
+            e1.record()
+            ev.append((e0, e1))
+        torch.cuda.synchronize()
+        res[mode] = sum(a.elapsed_time(b) for a, b in ev) / steps * 1e3
+    print("cfg1 one 1080p frame -> 1024^2: warm %.1f us, cold (L2 flushed) %.1f us per call" % (res["warm"], res["cold"]))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "cfg4":
         if len(sys.argv) > 3:
@@ -264,6 +293,8 @@ if __name__ == "__main__":
         if len(sys.argv) > 2:
             _native.set_warp_path(sys.argv[2])
         cams_uniform()
+    elif len(sys.argv) > 1 and sys.argv[1] == "cfg1":
+        cfg1_cold_warm()
     elif len(sys.argv) > 1 and sys.argv[1] == "host1":
         host_single()
     elif len(sys.argv) > 1 and sys.argv[1] == "iou":
