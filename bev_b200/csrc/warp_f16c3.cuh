@@ -23,6 +23,7 @@ struct PxF16C3 {
     static constexpr int kBpp = 6;
     static constexpr int kSegBytes = 192;
     static constexpr int kDtype = BEVK_F16;
+    static constexpr bool kPairs = false;
     using Reg = PixF16;
     struct Out {
         uint32_t x, y;  // halves [c0, c1], [c2, -]
@@ -51,6 +52,11 @@ struct PxF16C3 {
             q.w01 = q.w10 = q.w11 = 0.0f;
         }
         return q;
+    }
+    template <bool LINEAR> static __device__ __forceinline__ Reg make(bool act, uint32_t A, uint32_t wpk)
+    {
+        return make<LINEAR>(act, A, (int)(wpk & 0xffu), (int)((wpk >> 8) & 0xffu), (int)((wpk >> 16) & 0xffu),
+                            (int)(wpk >> 24));
     }
     // bilinear: 12 window bytes from an even offset span 4 words when the offset is 2 (mod 4);
     // nearest: 6 bytes always fit two words

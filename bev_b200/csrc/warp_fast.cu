@@ -115,6 +115,24 @@ struct ChunkPlan {
     uint32_t cum[kMaxChunks + 1];  // cum[0] = 0, cum[n_chunks] = 65536
 };
 
+// Per-launch scratch (stream-ordered allocation, see bevk_launch_warp_fast): the item counter and,
+// when a tile is worked on in several frame chunks, the set-up of every (group, tile) -- computed
+// by the CTA that runs the tile's first chunk, published through `ready`, re-used by the others.
+constexpr int kRecWords = 8;   // per thread: 4 pixels x (window position, packed weights)
+constexpr int kHdrInts = 8;    // per tile : source bounding box, "any pixel inside" flag
+struct WarpScratch {
+    int *next_item;   // zeroed
+    int *ready;       // [groups * tiles], zeroed; NULL: every item computes its own set-up
+    int *hdr;         // [groups * tiles][kHdrInts]
+    uint32_t *rec;    // [groups * tiles][kRecWords][kThreads]
+    int no_pairs;     // tuning aid (BEVK_NO_PAIRS): every warp takes the per-pixel path
+    int dbg;          // experiments (BEVK_DBG): 1 = no stores, 2 = no TMA traffic / waits (results are garbage)
+    int slack;        // ring stages NOT in flight ahead of the consumers (0: half the ring)
+    int pf;           // L2 prefetch distance in stages beyond the fills (-1: depth-2 rings only, 2 stages)
+    int max_fps;      // frames per ring stage, at most
+    int y_group, y_stride;  // tile rows are walked in groups of y_group, group g at (g * y_stride) % n_groups
+};
+
 // ---- PTX wrappers -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
@@ -171,6 +189,16 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr)
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ int ld_acquire(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 // Stops the compiler from re-deriving a loop-invariant value inside the frame loop.
 __device__ __forceinline__ void keep(uint32_t &v) { asm volatile("" : "+r"(v)); }
 
@@ -183,6 +211,7 @@ struct BoxPlan {
     int frame0, frame_step; // source frame of the item's frame i = frame0 + i * frame_step
     int src_h;
     int n_frames, fps;      // frames of the item / per ring stage
+    int slog;               // log2 of the ring depth in use
     uint32_t ring, full0;   // shared-memory addresses: ring, first barrier of the set in use
     uint32_t stride, frame_bytes, pitch;  // bytes per stage / staged frame / staged row
     int map_idx[kMaxBoxes];
@@ -195,10 +224,11 @@ struct ItemDesc {
     int gi, tile_x, tile_y;   // homography group, tile position
     int f0, n_frames;         // frames [f0, f0 + n_frames) of the group's run
     int first, stride;        // the run: frame index = first + f * stride
+    int chunk;                // frame chunk; chunk 0 computes (and publishes) the tile's set-up
 };
 
-// The consumers' loop state (kept small so that the frame loop fits 64 registers); the elected
-// producer lane reads what it needs from the BoxPlan in shared memory.
+// The consumers' loop state (kept small so that the frame loop fits its register budget); the
+// elected producer lane reads what it needs from the BoxPlan in shared memory.
 struct LoopCtx {
     uint32_t ring, full0;          // shared-memory addresses of the ring / first barrier of the set
     uint32_t stride;               // bytes per stage (fps frames)
@@ -206,6 +236,10 @@ struct LoopCtx {
     uint32_t pitch;                // bytes per staged row
     int fps;                       // frames per stage
     int n_frames;
+    int slog;                      // ring depth 2^slog stages
+    int ahead;                     // stages in flight ahead of the one being consumed
+    int pf;                        // L2 prefetch distance in stages beyond that (0: none)
+    int dbg;
     const WarpFastMaps *maps;
     const BoxPlan *plan;           // in shared memory
 };
@@ -216,7 +250,7 @@ struct LoopCtx {
 // copy does not wait on HBM (used by depth-2 rings, whose copies run just one stage ahead).
 // Deliberately not inlined: it runs in one lane of one warp per stage and must not cost the
 // frame loop registers.
-template <int SLOG, bool TO_SMEM>
+template <bool TO_SMEM>
 __device__ __noinline__ void produce(const BoxPlan *plan, const WarpFastMaps *maps, int i0,
                                      uint32_t use)
 {
@@ -226,10 +260,10 @@ __device__ __noinline__ void produce(const BoxPlan *plan, const WarpFastMaps *ma
     int y = (pl.frame0 + i0 * pl.frame_step) * pl.src_h + pl.y0;
     const int y_step = pl.frame_step * pl.src_h;
     if (TO_SMEM) {
-        const uint32_t slot = use & ((1u << SLOG) - 1u);
+        const uint32_t slot = use & ((1u << pl.slog) - 1u);
         const uint32_t fb = pl.full0 + 8 * slot;
         // k-th fill of a slot waits for the (k-1)-th release; the first passes at once
-        mbar_wait(fb + (8u << SLOG), ((use >> SLOG) & 1u) ^ 1u);
+        mbar_wait(fb + (8u << pl.slog), ((use >> pl.slog) & 1u) ^ 1u);
         mbar_expect_tx(fb, pl.bytes * nf);
         uint32_t sdst = pl.ring + slot * pl.stride;
 #pragma unroll 1
@@ -251,75 +285,116 @@ __device__ __noinline__ void produce(const BoxPlan *plan, const WarpFastMaps *ma
 // item consumed up to and including the current stage.  The producer role rotates over the warps
 // (one elected lane each) so that no warp is slower than the others -- a fixed producer warp
 // paces the whole CTA, because every warp waits on the stages it issues.
-template <int SLOG>
 __device__ __forceinline__ void feed(const LoopCtx &c, int done, uint32_t use, int lane, int warp)
 {
-    constexpr int ahead = 1 << (SLOG - 1);
     if (lane != 0) return;
     const int turn = ((int)use - warp) & (kWarps - 1);
-    const int i_load = done + (ahead - 1) * c.fps;  // first frame of the stage `ahead` stages on
-    if (turn == 0 && i_load < c.n_frames) produce<SLOG, true>(c.plan, c.maps, i_load, use + ahead);
-    if (SLOG == 1 && turn == kWarps / 2 && i_load + kPrefetchAhead * c.fps < c.n_frames)
-        produce<SLOG, false>(c.plan, c.maps, i_load + kPrefetchAhead * c.fps, 0);
+    const int i_load = done + (c.ahead - 1) * c.fps;  // first frame of the stage `ahead` stages on
+    if (turn == 0 && i_load < c.n_frames) produce<true>(c.plan, c.maps, i_load, use + c.ahead);
+    if (c.pf && turn == kWarps / 2 && i_load + c.pf * c.fps < c.n_frames)
+        produce<false>(c.plan, c.maps, i_load + c.pf * c.fps, 0);
 }
 
-// The frame loop of a staged item.  Ring depth 2^SLOG stages of c.fps frames each.  Returns the
-// advanced stage counter.  PX = pixel format policy (warp_u8c3.cuh / warp_f16c3.cuh).
-template <typename PX, bool LINEAR, int SLOG, int SEGS>
-__device__ __forceinline__ uint32_t frame_loop(const LoopCtx &c, const typename PX::Reg (&px)[4],
-                                               uint32_t use, uint8_t *d, const uint32_t d_step,
-                                               const uint32_t row_bytes, const bool (&seg_ok)[4],
-                                               const typename PX::Store st, const int tid)
+// The frame loop of a staged item: ring of 2^slog stages of c.fps frames each, half of them in
+// flight ahead of the stage being consumed -- the other half is slack between the warps (a slot is
+// refilled S/2 stages after its last use, so the refilling lane practically never waits for a
+// slower warp to release it).  body(sa, d, release) interpolates the thread's pixels of ONE frame
+// staged at shared address sa into d; it calls release() once all its shared-memory reads are
+// issued.  Returns the advanced stage counter.
+template <typename BODY>
+__device__ __forceinline__ uint32_t stage_loop(const LoopCtx &c, uint32_t use, uint8_t *d,
+                                               const uint32_t d_step, const int tid, BODY body)
 {
-    constexpr uint32_t smask = (1u << SLOG) - 1u;
-    // Stages in flight besides the one being consumed: half the ring.  The other half is slack
-    // between the warps -- a slot is refilled S/2 stages after its last use, so the refilling lane
-    // practically never waits for a slower warp to release it.
-    constexpr int ahead = 1 << (SLOG - 1);
-    constexpr uint32_t kLast = PX::template last_word_offset<LINEAR>();
+    const uint32_t smask = (1u << c.slog) - 1u;
     const int lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
-        for (int s = 0; s < ahead && s * c.fps < c.n_frames; ++s)
-            produce<SLOG, true>(c.plan, c.maps, s * c.fps, use + s);
-        if (SLOG == 1)
-            for (int s = ahead; s < ahead + kPrefetchAhead && s * c.fps < c.n_frames; ++s)
-                produce<SLOG, false>(c.plan, c.maps, s * c.fps, 0);
+    if (tid == 0 && !(c.dbg & 2)) {
+        for (int s = 0; s < c.ahead && s * c.fps < c.n_frames; ++s)
+            produce<true>(c.plan, c.maps, s * c.fps, use + s);
+        for (int s = c.ahead; s < c.ahead + c.pf && s * c.fps < c.n_frames; ++s)
+            produce<false>(c.plan, c.maps, s * c.fps, 0);
     }
-
     int done = 0;
 #pragma unroll 1
     while (done < c.n_frames) {
         const uint32_t slot = use & smask;
         const uint32_t fb = c.full0 + 8 * slot;
-        mbar_wait(fb, (use >> SLOG) & 1u);
-        uint32_t sa = c.ring + slot * c.stride;  // row 0 of the windows, first frame of the stage
+        if (!(c.dbg & 2)) mbar_wait(fb, (use >> c.slog) & 1u);
+        uint32_t sa = c.ring + slot * c.stride;  // first frame of the stage
         int nf = min(c.fps, c.n_frames - done);
         done += nf;
 #pragma unroll 1
         for (; nf > 0; --nf, sa += c.frame_bytes, d += d_step) {
-            const uint32_t sb = sa + c.pitch;  // row 1
-            typename PX::Out P[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                uint32_t w[8];
-                const uint32_t a = px[k].addr + sa, b = px[k].addr + sb;
-                PX::template load<LINEAR>(px[k], a, b, a + kLast, b + kLast, w, [](uint32_t ad) { return lds32(ad); });
-                if (k == 3 && nf == 1) {
+            body(sa, d, [&]() {
+                if (nf == 1 && !(c.dbg & 2)) {
                     // every shared-memory read of this stage is issued: hand the slot back
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(fb + (8u << SLOG));
-                    feed<SLOG>(c, done, use, lane, warp);
+                    if (lane == 0) mbar_arrive(fb + (8u << c.slog));
+                    // (through keep(): whose turn it is gets worked out here, once per stage, and
+                    // not hoisted into predicates that stay live across the frame loop)
+                    uint32_t u = use, dn = (uint32_t)done;
+                    keep(u);
+                    keep(dn);
+                    feed(c, (int)dn, u, lane, warp);
                 }
-                P[k] = PX::template math<LINEAR>(px[k], w);
-            }
-            // pack the lanes' pixels into words and store coalesced row segments
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                PX::store(d + PX::kSegBytes * (k % SEGS) + (k / SEGS) * row_bytes, P[k], seg_ok[k], st, lane);
+            });
         }
         ++use;
     }
     return use;
+}
+
+// ---- which dst pixels a thread owns ---------------------------------------------------------------
+// A warp owns two adjacent dst rows x 64 columns (SEGS >= 2) or four rows x 32 columns (SEGS == 1);
+// thread pixel k = 2 j + i is row i of vertical PAIR j: the two pixels of a pair are vertical
+// neighbours, so wherever the map magnifies vertically their 2x2 source windows overlap and the
+// pair path below loads the window rows once for both.
+template <int SEGS> __device__ __forceinline__ int warp_px_x(int warp)
+{
+    return SEGS >= 2 ? 64 * (warp % (SEGS >= 2 ? SEGS / 2 : 1)) : 0;
+}
+template <int SEGS> __device__ __forceinline__ int warp_px_y(int warp)
+{
+    return SEGS >= 2 ? 2 * (warp / (SEGS >= 2 ? SEGS / 2 : 1)) : 4 * warp;
+}
+template <int SEGS> __device__ __forceinline__ constexpr int px_seg(int k) { return SEGS >= 2 ? (k >> 1) : 0; }
+template <int SEGS> __device__ __forceinline__ constexpr int px_row(int k) { return SEGS >= 2 ? (k & 1) : k; }
+
+// Frame-invariant registers of a vertical pixel pair that shares its window loads (uint8 x 3,
+// bilinear).  `first` is the pixel whose window starts on the pair's first source row; the second
+// one's starts on the same row (2-row variant) or one row below (3-row variant).  Columns: the
+// pair's 12-byte span per row starts at the smaller of the two window columns, a pixel's window
+// starts 0 or 3 bytes into it.
+struct PairReg {
+    uint32_t addr;         // byte offset (4-aligned) inside a staged frame of the span, first row
+    uint32_t sh, shv;      // funnel-shift amounts: 8 * (start & 3), 8 * ((start + 2) & 3)
+    uint32_t sel_f, sel_s; // PRMT selector of the first / second pixel: window at byte 0 or 3
+    uint32_t wf0, wf1;     // dp2a tap weights of the first pixel, its window rows 0 / 1
+    uint32_t ws0, ws1;     // ... of the second pixel
+};
+
+// One staged row of a pair's span: byte-align it (g0 = bytes 0..3, g1 = 4..7) and put the bytes
+// the third channel of either window needs where one selector serves both PRMTs:
+//   window at byte 0 (selector 0x4130): xa = [b0 b3 b1 b4]  ya = [b2 b5 . .]
+//   window at byte 3 (selector 0x7463): xa = [b3 b6 b4 b7]  ya = [b5 b8 . .]
+// with ya = prmt(u, v, sel), u = [b2 . . b5], v = [. . b8 .].
+struct PairRow {
+    uint32_t g0, g1, u, v;
+};
+__device__ __forceinline__ PairRow pair_row(uint32_t a, uint32_t sh, uint32_t shv)
+{
+    const uint32_t w0 = lds32(a), w1 = lds32(a + 4), w2 = lds32(a + 8);
+    PairRow r;
+    r.g0 = __funnelshift_r(w0, w1, sh);
+    r.g1 = __funnelshift_r(w1, w2, sh);
+    r.v = __funnelshift_r(w2, w2, shv);  // byte 2 = span byte 8
+    r.u = prmt(r.g0, r.g1, 0x5002u);
+    return r;
+}
+__device__ __forceinline__ uint32_t pair_lerp(const PairRow &r0, const PairRow &r1, uint32_t sel, uint32_t w0,
+                                              uint32_t w1)
+{
+    return lerp_xy(w0, w1, prmt(r0.g0, r0.g1, sel), prmt(r0.u, r0.v, sel), prmt(r1.g0, r1.g1, sel),
+                   prmt(r1.u, r1.v, sel));
 }
 
 // MINB = CTAs per SM the register allocation is bounded for (4 -> 64 registers, 3 -> 80);
@@ -329,7 +404,7 @@ __global__ void __launch_bounds__(kThreads, MINB)
 warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
                       const __grid_constant__ WarpFastMaps maps,
                       const __grid_constant__ ChunkPlan plan, const int tiles_x, const int tiles_y,
-                      const int total_items, const int ring_bytes, int *const next_item)
+                      const int total_items, const int ring_bytes, const WarpScratch sc)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     // three barrier sets, one per ring depth S = 2, 4, 8: full[S] then empty[S], at byte
@@ -357,7 +432,6 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
 
     const int n_tiles = tiles_x * tiles_y;
     const uint8_t *src = (const uint8_t *)p.src;
@@ -367,9 +441,10 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
     const long long src_frame_bytes = (long long)src_row_bytes * p.src_h;
     const long long dst_frame_bytes = (long long)p.dst_w * p.dst_h * kBpp;
 
-    // Items are (chunk, group, tile) with the chunk index slowest: long chunks first.  The first
-    // gridDim.x items are taken by block index, the rest are pulled from *next_item.  Thread 0
-    // decodes an item (integer divisions, parameter reads) one item ahead of its use.
+    // Items are (chunk, group, tile) with the chunk index slowest: long chunks first.  Every item
+    // is pulled from *sc.next_item -- also a CTA's first one, so that a CTA which has not started
+    // yet never holds a tile's first chunk while others wait for its set-up.  Thread 0 decodes an
+    // item (integer divisions, parameter reads) one item ahead of its use.
     const int per_chunk = p.n_groups * n_tiles;
     auto decode = [&](int item, ItemDesc &o) {
         o.item = item;
@@ -380,22 +455,28 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
         // magnified far field (store-heavy) and the minified near field (load-heavy)
         o.gi = gi;
         o.tile_x = tile / tiles_y;
-        o.tile_y = tile - o.tile_x * tiles_y;
+        const int ty = tile - o.tile_x * tiles_y;
+        // ... with the tile rows of a column permuted by a stride, so that the CTAs that share an
+        // SM (consecutive items) work on different zones of the map at any time
+        const int yg = ty / sc.y_group;
+        o.tile_y = (int)(((long long)yg * sc.y_stride) % (tiles_y / sc.y_group)) * sc.y_group + (ty - yg * sc.y_group);
         const int count = p.g[gi].count;
         o.f0 = (int)(((unsigned long long)count * plan.cum[chunk]) >> 16);
         o.n_frames = (int)(((unsigned long long)count * plan.cum[chunk + 1]) >> 16) - o.f0;
         o.first = p.g[gi].first;
         o.stride = p.g[gi].stride;
+        o.chunk = chunk;
     };
     for (int i = tid; i < p.n_groups * 9; i += kThreads) s_M[i / 9][i % 9] = p.g[i / 9].M[i % 9];
     if (tid == 0) {
-        decode(blockIdx.x, s_item[0]);
+        decode(atomicAdd(sc.next_item, 1), s_item[0]);
         s_box[0] = s_box[2] = 1 << 30;
         s_box[1] = s_box[3] = -1;
         s_any = 0;
     }
     __syncthreads();
     const bool bw0_pow2 = (p.bw0 & (p.bw0 - 1)) == 0;
+    const uint32_t row_bytes = (uint32_t)p.dst_w * (uint32_t)kBpp;
 
     int par = 0;
 #pragma unroll 1
@@ -405,63 +486,103 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
         const int gi = s_item[par].gi, tile_x = s_item[par].tile_x, tile_y = s_item[par].tile_y;
         const int f0 = s_item[par].f0, n_frames = s_item[par].n_frames;
         const int g_first = s_item[par].first, g_stride = s_item[par].stride;
-        constexpr int kRowsPerWarp = 4 / SEGS;
-        const int x0 = tile_x * tile_w(SEGS), y0 = tile_y * tile_h(SEGS) + warp * kRowsPerWarp;
-        const uint32_t row_bytes = (uint32_t)p.dst_w * (uint32_t)kBpp;
+        const int chunk = s_item[par].chunk;
+        const int x0 = tile_x * tile_w(SEGS) + warp_px_x<SEGS>(warp);
+        const int y0 = tile_y * tile_h(SEGS) + warp_px_y<SEGS>(warp);
+        const int tile_id = gi * n_tiles + tile_x * tiles_y + tile_y;
         par ^= 1;
 
-        // ---- 1. set-up ------------------------------------------------------------------------
-        int cs[4], rs[4], wc0[4], wc1[4], wr0[4], wr1[4];
-        int bx0 = 1 << 30, bx1 = -1, by0 = 1 << 30, by1 = -1;
+        // ---- 1. set-up: window position and tap weights of the thread's four pixels, the tile's
+        //         source bounding box -- computed by the tile's first chunk, re-read by the others
+        int cs[4], rs[4];
+        uint32_t wpk[4];  // wc0 | wc1 << 8 | wr0 << 16 | wr1 << 24 (0..32 each); 0 = pixel inactive
+        int bx0, bx1, by0, by1;
+        bool any;
+        if (sc.ready == nullptr || chunk == 0) {
+            bx0 = by0 = 1 << 30;
+            bx1 = by1 = -1;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int x = x0 + lane + 32 * (k % SEGS), y = y0 + k / SEGS;
-            const bool in_dst = (x < p.dst_w) && (y < p.dst_h);
-            int X, Y;
-            const int xc = min(x, p.dst_w - 1);
-            const int xb = bw0_pow2 ? (xc & ~(p.bw0 - 1)) : (xc / p.bw0) * p.bw0;
-            bevk_map_pixel_xb(s_M[gi], xb, xc - xb, min(y, p.dst_h - 1), LINEAR ? 32.0 : 1.0, X, Y);
-            if (LINEAR) {
-                const int sx = bevk_sat16(X >> 5), sy = bevk_sat16(Y >> 5);
-                window(sx, X & 31, p.src_w, cs[k], wc0[k], wc1[k]);
-                window(sy, Y & 31, p.src_h, rs[k], wr0[k], wr1[k]);
-            } else {
-                const int sx = bevk_sat16(X), sy = bevk_sat16(Y);
-                const bool in = sx >= 0 && sx < p.src_w && sy >= 0 && sy < p.src_h;
-                cs[k] = min(max(sx, 0), p.src_w - 1);
-                rs[k] = min(max(sy, 0), p.src_h - 1);
-                wc0[k] = in ? 1 : 0;
-                wc1[k] = 0;
-                wr0[k] = in ? 1 : 0;
-                wr1[k] = 0;
+            for (int k = 0; k < 4; ++k) {
+                const int x = x0 + lane + 32 * px_seg<SEGS>(k), y = y0 + px_row<SEGS>(k);
+                const bool in_dst = (x < p.dst_w) && (y < p.dst_h);
+                int X, Y, wc0, wc1, wr0, wr1;
+                const int xc = min(x, p.dst_w - 1);
+                const int xb = bw0_pow2 ? (xc & ~(p.bw0 - 1)) : (xc / p.bw0) * p.bw0;
+                bevk_map_pixel_xb(s_M[gi], xb, xc - xb, min(y, p.dst_h - 1), LINEAR ? 32.0 : 1.0, X, Y);
+                if (LINEAR) {
+                    const int sx = bevk_sat16(X >> 5), sy = bevk_sat16(Y >> 5);
+                    window(sx, X & 31, p.src_w, cs[k], wc0, wc1);
+                    window(sy, Y & 31, p.src_h, rs[k], wr0, wr1);
+                } else {
+                    const int sx = bevk_sat16(X), sy = bevk_sat16(Y);
+                    const bool in = sx >= 0 && sx < p.src_w && sy >= 0 && sy < p.src_h;
+                    cs[k] = min(max(sx, 0), p.src_w - 1);
+                    rs[k] = min(max(sy, 0), p.src_h - 1);
+                    wc0 = wr0 = in ? 1 : 0;
+                    wc1 = wr1 = 0;
+                }
+                const bool active = in_dst && (wc0 | wc1) != 0 && (wr0 | wr1) != 0;
+                wpk[k] = active ? (uint32_t)(wc0 | (wc1 << 8) | (wr0 << 16) | (wr1 << 24)) : 0u;
+                if (active) {
+                    bx0 = min(bx0, cs[k]);
+                    bx1 = max(bx1, cs[k] + (LINEAR ? 1 : 0));
+                    by0 = min(by0, rs[k]);
+                    by1 = max(by1, rs[k] + (LINEAR ? 1 : 0));
+                }
             }
-            const bool active = in_dst && (wc0[k] | wc1[k]) != 0 && (wr0[k] | wr1[k]) != 0;
-            if (!active) {
-                wc0[k] = wc1[k] = wr0[k] = wr1[k] = 0;
-            } else {
-                bx0 = min(bx0, cs[k]);
-                bx1 = max(bx1, cs[k] + (LINEAR ? 1 : 0));
-                by0 = min(by0, rs[k]);
-                by1 = max(by1, rs[k] + (LINEAR ? 1 : 0));
+            bx0 = __reduce_min_sync(0xffffffffu, bx0);
+            bx1 = __reduce_max_sync(0xffffffffu, bx1);
+            by0 = __reduce_min_sync(0xffffffffu, by0);
+            by1 = __reduce_max_sync(0xffffffffu, by1);
+            if (lane == 0 && bx1 >= 0) {
+                atomicMin(&s_box[0], bx0);
+                atomicMax(&s_box[1], bx1);
+                atomicMin(&s_box[2], by0);
+                atomicMax(&s_box[3], by1);
+                s_any = 1;
+            }
+            __syncthreads();
+            any = s_any != 0;
+            bx0 = s_box[0];
+            bx1 = s_box[1];
+            by0 = s_box[2];
+            by1 = s_box[3];
+            if (sc.ready != nullptr) {
+                uint32_t *rec = sc.rec + (size_t)tile_id * (kRecWords * kThreads) + tid;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    __stcg(rec + (2 * k) * kThreads, (uint32_t)cs[k] | ((uint32_t)rs[k] << 16));
+                    __stcg(rec + (2 * k + 1) * kThreads, wpk[k]);
+                }
+                if (tid == 0) {
+                    int4 *h = reinterpret_cast<int4 *>(sc.hdr + (size_t)tile_id * kHdrInts);
+                    __stcg(h, make_int4(bx0, bx1, by0, by1));
+                    __stcg(h + 1, make_int4(any ? 1 : 0, 0, 0, 0));
+                }
+                __threadfence();  // ordered before the release store that follows the next barrier
+            }
+        } else {
+            if (tid == 0) {
+                const int *flag = sc.ready + tile_id;
+                while (ld_acquire(flag) == 0) __nanosleep(100);
+            }
+            __syncthreads();
+            const int4 *h = reinterpret_cast<const int4 *>(sc.hdr + (size_t)tile_id * kHdrInts);
+            const int4 hb = __ldcg(h), hf = __ldcg(h + 1);
+            bx0 = hb.x;
+            bx1 = hb.y;
+            by0 = hb.z;
+            by1 = hb.w;
+            any = hf.x != 0;
+            const uint32_t *rec = sc.rec + (size_t)tile_id * (kRecWords * kThreads) + tid;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t pos = __ldcg(rec + (2 * k) * kThreads);
+                cs[k] = (int)(pos & 0xffffu);
+                rs[k] = (int)(pos >> 16);
+                wpk[k] = __ldcg(rec + (2 * k + 1) * kThreads);
             }
         }
-        bx0 = __reduce_min_sync(0xffffffffu, bx0);
-        bx1 = __reduce_max_sync(0xffffffffu, bx1);
-        by0 = __reduce_min_sync(0xffffffffu, by0);
-        by1 = __reduce_max_sync(0xffffffffu, by1);
-        if (lane == 0 && bx1 >= 0) {
-            atomicMin(&s_box[0], bx0);
-            atomicMax(&s_box[1], bx1);
-            atomicMin(&s_box[2], by0);
-            atomicMax(&s_box[3], by1);
-            s_any = 1;
-        }
-        __syncthreads();
-        const bool any = s_any != 0;
-        bx0 = s_box[0];
-        bx1 = s_box[1];
-        by0 = s_box[2];
-        by1 = s_box[3];
 
         // staged geometry: 16-byte aligned first column, box shapes from the tensor-map menu
         const int a0 = (kBpp * bx0) & ~15;
@@ -484,9 +605,11 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
         // staged for nothing (and fetched from HBM for nothing) -- gather those tiles directly
         if (!LINEAR && frame_bytes > 3u * 1024u * (uint32_t)kBpp) staged = false;
         // frames per stage: as many as still leave a ring of 4 stages
-        const int fps = (4 * kMaxStageFrames * frame_bytes <= (uint32_t)ring_bytes)
-                            ? kMaxStageFrames
-                            : (8 * frame_bytes <= (uint32_t)ring_bytes ? 2 : 1);
+        const int fps = (4 * 8 * frame_bytes <= (uint32_t)ring_bytes && sc.max_fps >= 8)
+                            ? 8
+                            : ((4 * 4 * frame_bytes <= (uint32_t)ring_bytes && sc.max_fps >= 4)
+                                   ? 4
+                                   : (8 * frame_bytes <= (uint32_t)ring_bytes && sc.max_fps >= 2 ? 2 : 1));
         const int stage_stride = fps * (int)frame_bytes;
         const int slog = (8 * stage_stride <= ring_bytes) ? 3 : (4 * stage_stride <= ring_bytes ? 2 : 1);
         const uint32_t full0 = bar0 + 16 * (1 << slog) - 32;  // the set's empty[] follow its full[]
@@ -510,6 +633,7 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
                 s_plan.src_h = p.src_h;
                 s_plan.n_frames = n_frames;
                 s_plan.fps = fps;
+                s_plan.slog = slog;
                 s_plan.ring = ring;
                 s_plan.full0 = full0;
                 s_plan.stride = stage_stride;
@@ -519,13 +643,14 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
         }
         __syncthreads();  // s_plan visible to the producer lanes; every thread has read s_box
         if (tid == 0) {
+            // the tile's set-up is in global memory (every thread fenced its part before the barrier)
+            if (sc.ready != nullptr && chunk == 0) st_release(sc.ready + tile_id, 1);
             // re-arm the box for the next item (its first atomics come after this item's last
             // barrier), then fetch + decode the next item: nobody waits for thread 0 until then
             s_box[0] = s_box[2] = 1 << 30;
             s_box[1] = s_box[3] = -1;
             s_any = 0;
-            decode(next_item ? (int)gridDim.x + atomicAdd(next_item, 1) : item + (int)gridDim.x,
-                   s_item[par]);
+            decode(atomicAdd(sc.next_item, 1), s_item[par]);
         }
 
         // ---- store geometry ---------------------------------------------------------------------
@@ -535,9 +660,16 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             // pixels left in this 32-pixel segment: a multiple of 4 (dst_w % 4 == 0)
-            const int valid_px = min(32, p.dst_w - (x0 + 32 * (k % SEGS)));
-            seg_ok[k] = (y0 + k / SEGS < p.dst_h) && PX::lane_stores(lane, valid_px);
+            const int valid_px = min(32, p.dst_w - (x0 + 32 * px_seg<SEGS>(k)));
+            seg_ok[k] = (y0 + px_row<SEGS>(k) < p.dst_h) && PX::lane_stores(lane, valid_px);
         }
+        // where pixel k's segment goes, from the thread's pointer into dst row y0 (dd) and the one
+        // into row y0 + 1 (dd1): compile-time segment offsets, one runtime row step
+        auto seg_ptr = [row_bytes](uint8_t *dd, uint8_t *dd1, int k) -> uint8_t * {
+            if (SEGS >= 2) return (px_row<SEGS>(k) ? dd1 : dd) + PX::kSegBytes * px_seg<SEGS>(k);
+            return (k & 1 ? dd1 : dd) + (k >> 1) * 2 * (size_t)row_bytes;
+        };
+        if (sc.dbg & 1) seg_ok[0] = seg_ok[1] = seg_ok[2] = seg_ok[3] = false;
         uint32_t d_step = (uint32_t)g_stride * (uint32_t)dst_frame_bytes;  // < 2^32 (host check)
         keep(d_step);
         uint8_t *d = dst + (long long)(g_first + f0 * g_stride) * dst_frame_bytes +
@@ -548,18 +680,8 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
 #pragma unroll 1
             for (int i = 0; i < n_frames; ++i, d += d_step)
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    PX::store_zero(d + PX::kSegBytes * (k % SEGS) + (k / SEGS) * row_bytes, seg_ok[k], lane);
+                for (int k = 0; k < 4; ++k) PX::store_zero(seg_ptr(d, d + row_bytes, k), seg_ok[k], lane);
         } else if (staged) {
-            typename PX::Reg px[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const bool act = (wc0[k] | wc1[k]) != 0;
-                const int A = act ? (rs[k] - by0) * pitch + kBpp * cs[k] - a0 : 0;
-                px[k] = PX::template make<LINEAR>(act, (uint32_t)A, wc0[k], wc1[k], wr0[k], wr1[k]);
-                keep(px[k].addr);
-                keep(px[k].sh);
-            }
             LoopCtx c;
             c.ring = ring;
             c.full0 = full0;
@@ -568,24 +690,160 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
             c.pitch = pitch;
             c.fps = fps;
             c.n_frames = n_frames;
+            c.slog = slog;
+            c.ahead = sc.slack ? max(1, (1 << slog) - sc.slack) : (1 << (slog - 1));
+            c.pf = sc.pf >= 0 ? sc.pf : (slog == 1 ? kPrefetchAhead : 0);
+            c.dbg = sc.dbg;
             c.maps = &maps;
             c.plan = &s_plan;
             keep(c.ring);
             keep(c.full0);
             // every thread tracks the counter in a register; thread 0 publishes it for the next item
             uint32_t use = s_use[slog - 1];
-            if (slog == 3)
-                use = frame_loop<PX, LINEAR, 3, SEGS>(c, px, use, d, d_step, row_bytes, seg_ok, st, tid);
-            else if (slog == 2)
-                use = frame_loop<PX, LINEAR, 2, SEGS>(c, px, use, d, d_step, row_bytes, seg_ok, st, tid);
-            else
-                use = frame_loop<PX, LINEAR, 1, SEGS>(c, px, use, d, d_step, row_bytes, seg_ok, st, tid);
+
+            // Pair path (uint8 x 3 bilinear): can every vertical pair of this warp share its
+            // window loads?  Needs windows at most one column apart and the same row step --
+            // 0 (both on the same two rows), +1 or -1 (the second / first pixel of the pair one
+            // row below) -- across the warp, so that the choice of window rows is warp-uniform.
+            int var = 3;
+            if constexpr (LINEAR && PX::kPairs) {
+                bool ok0 = true, ok1 = true, ok2 = true;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int a = 2 * j, b = a + 1;
+                    const bool aa = wpk[a] != 0, ab = wpk[b] != 0;
+                    if (aa && ab) {
+                        const int dr = rs[b] - rs[a], dc = cs[b] - cs[a];
+                        const bool near = dc >= -1 && dc <= 1;
+                        ok0 = ok0 && near && dr == 0;
+                        ok1 = ok1 && near && dr == 1;
+                        ok2 = ok2 && near && dr == -1;
+                    } else if (aa || ab) {
+                        // one active pixel: it can take either role as long as the pair's rows
+                        // stay inside the staged box
+                        const int r = aa ? rs[a] : rs[b];
+                        ok1 = ok1 && (aa ? r + 2 <= by1 : r - 1 >= by0);
+                        ok2 = ok2 && (ab ? r + 2 <= by1 : r - 1 >= by0);
+                    } else {
+                        ok1 = ok1 && by1 - by0 >= 2;
+                        ok2 = ok2 && by1 - by0 >= 2;
+                    }
+                }
+                if (sc.no_pairs) ok0 = ok1 = ok2 = false;
+                var = __all_sync(0xffffffffu, ok0) ? 0
+                      : (__all_sync(0xffffffffu, ok1) ? 1 : (__all_sync(0xffffffffu, ok2) ? 2 : 3));
+            }
+            if constexpr (LINEAR && PX::kPairs) if (var != 3) {
+                PairReg pr[2];
+                uint32_t ok = 0;  // store predicates as a bit mask: bit 2 j = first, 2 j + 1 = second pixel of pair j
+                const bool sw = var == 2;  // the pair's first pixel is the one in the lower dst row
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    // first / second pixel of the pair (explicit selects: no dynamically indexed arrays)
+                    const int rs_f = sw ? rs[2 * j + 1] : rs[2 * j], rs_s = sw ? rs[2 * j] : rs[2 * j + 1];
+                    const int cs_f = sw ? cs[2 * j + 1] : cs[2 * j], cs_s = sw ? cs[2 * j] : cs[2 * j + 1];
+                    const uint32_t wp_f = sw ? wpk[2 * j + 1] : wpk[2 * j], wp_s = sw ? wpk[2 * j] : wpk[2 * j + 1];
+                    const bool af = wp_f != 0, as = wp_s != 0;
+                    const int step = var ? 1 : 0;
+                    const int rf = af ? rs_f : (as ? rs_s - step : by0);
+                    const int cf = af ? cs_f : (as ? cs_s : bx0), cn = as ? cs_s : cf;
+                    const int c0 = min(cf, cn);
+                    const uint32_t A = (uint32_t)((rf - by0) * pitch + kBpp * c0 - a0);
+                    pr[j].addr = A & ~3u;
+                    pr[j].sh = 8 * (A & 3);
+                    pr[j].shv = 8 * ((A + 2) & 3);
+                    pr[j].sel_f = cf != c0 ? 0x7463u : 0x4130u;
+                    pr[j].sel_s = cn != c0 ? 0x7463u : 0x4130u;
+                    PxU8C3::tap_weights(wp_f, pr[j].wf0, pr[j].wf1);
+                    PxU8C3::tap_weights(wp_s, pr[j].ws0, pr[j].ws1);
+                    keep(pr[j].addr);
+                    keep(pr[j].sh);
+                    keep(pr[j].shv);
+                    keep(pr[j].sel_f);
+                    keep(pr[j].sel_s);
+                    ok |= ((sw ? seg_ok[2 * j + 1] : seg_ok[2 * j]) ? 1u : 0u) << (2 * j);
+                    ok |= ((sw ? seg_ok[2 * j] : seg_ok[2 * j + 1]) ? 2u : 0u) << (2 * j);
+                }
+                keep(ok);
+                const long long d_second = sw ? -(long long)row_bytes : (long long)row_bytes;
+                uint8_t *d_first = sw ? d + row_bytes : d;
+                if (var == 0) {
+                    use = stage_loop(c, use, d_first, d_step, tid, [&](uint32_t sa, uint8_t *dd, auto release) {
+                        const uint32_t sb = sa + c.pitch;
+                        uint32_t P[4];
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const PairRow r0 = pair_row(pr[j].addr + sa, pr[j].sh, pr[j].shv);
+                            const PairRow r1 = pair_row(pr[j].addr + sb, pr[j].sh, pr[j].shv);
+                            if (j == 1) release();
+                            P[2 * j] = pair_lerp(r0, r1, pr[j].sel_f, pr[j].wf0, pr[j].wf1);
+                            P[2 * j + 1] = pair_lerp(r0, r1, pr[j].sel_s, pr[j].ws0, pr[j].ws1);
+                        }
+                        // dd points into the first pixels' dst row, the second pixels' is one row on / back
+                        uint8_t *ds = dd + d_second;
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            PX::store(seg_ptr(dd, dd, 2 * j), P[2 * j], (ok >> (2 * j)) & 1u, st, lane);
+                            PX::store(seg_ptr(ds, ds, 2 * j), P[2 * j + 1], (ok >> (2 * j + 1)) & 1u, st, lane);
+                        }
+                    });
+                } else {
+                    use = stage_loop(c, use, d_first, d_step, tid, [&](uint32_t sa, uint8_t *dd, auto release) {
+                        const uint32_t sb = sa + c.pitch, sc2 = sb + c.pitch;
+                        uint32_t P[4];
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const PairRow r0 = pair_row(pr[j].addr + sa, pr[j].sh, pr[j].shv);
+                            const PairRow r1 = pair_row(pr[j].addr + sb, pr[j].sh, pr[j].shv);
+                            const PairRow r2 = pair_row(pr[j].addr + sc2, pr[j].sh, pr[j].shv);
+                            if (j == 1) release();
+                            P[2 * j] = pair_lerp(r0, r1, pr[j].sel_f, pr[j].wf0, pr[j].wf1);
+                            P[2 * j + 1] = pair_lerp(r1, r2, pr[j].sel_s, pr[j].ws0, pr[j].ws1);
+                        }
+                        // dd points into the first pixels' dst row, the second pixels' is one row on / back
+                        uint8_t *ds = dd + d_second;
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            PX::store(seg_ptr(dd, dd, 2 * j), P[2 * j], (ok >> (2 * j)) & 1u, st, lane);
+                            PX::store(seg_ptr(ds, ds, 2 * j), P[2 * j + 1], (ok >> (2 * j + 1)) & 1u, st, lane);
+                        }
+                    });
+                }
+            }
+            if (var == 3) {
+                constexpr uint32_t kLast = PX::template last_word_offset<LINEAR>();
+                typename PX::Reg px[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool act = wpk[k] != 0;
+                    const int A = act ? (rs[k] - by0) * pitch + kBpp * cs[k] - a0 : 0;
+                    px[k] = PX::template make<LINEAR>(act, (uint32_t)A, wpk[k]);
+                    keep(px[k].addr);
+                    keep(px[k].sh);
+                }
+                use = stage_loop(c, use, d, d_step, tid, [&](uint32_t sa, uint8_t *dd, auto release) {
+                    const uint32_t sb = sa + c.pitch;  // row 1 of the windows
+                    typename PX::Out P[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        uint32_t w[8];
+                        const uint32_t a = px[k].addr + sa, b = px[k].addr + sb;
+                        PX::template load<LINEAR>(px[k], a, b, a + kLast, b + kLast, w,
+                                                  [](uint32_t ad) { return lds32(ad); });
+                        if (k == 3) release();
+                        P[k] = PX::template math<LINEAR>(px[k], w);
+                    }
+                    // pack the lanes' pixels into words and store coalesced row segments
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) PX::store(seg_ptr(dd, dd + row_bytes, k), P[k], seg_ok[k], st, lane);
+                });
+            }
             __syncthreads();  // every warp has read s_use and left the ring
             if (tid == 0) s_use[slog - 1] = use;
             continue;
         } else if (p.hard) {
             // split launch: leave the tile to the direct-gather kernel that follows on the stream
-            if (tid == 0) p.hard[gi * p.hard_tiles + tile_x * tiles_y + tile_y] = 1;
+            if (tid == 0) p.hard[tile_id] = 1;
         } else {
             // bounding box too large for the ring (strong minification) or too wide / tall for the
             // tensor-map menu: the same arithmetic on aligned 32-bit loads straight from global
@@ -597,9 +855,9 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
             const uint32_t last_word = (uint32_t)src_frame_bytes - 4u;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const bool act = (wc0[k] | wc1[k]) != 0;
+                const bool act = wpk[k] != 0;
                 const uint32_t A = act ? (uint32_t)rs[k] * (uint32_t)src_row_bytes + (uint32_t)kBpp * (uint32_t)cs[k] : 0u;
-                px[k] = PX::template make<LINEAR>(act, A, wc0[k], wc1[k], wr0[k], wr1[k]);
+                px[k] = PX::template make<LINEAR>(act, A, wpk[k]);
                 // bilinear reads row 1 of the window at +src_row_bytes: clamp so that also that
                 // read stays inside the frame (the alignments that need the word never clamp)
                 last[k] = min(px[k].addr + kLast, last_word - (LINEAR ? (uint32_t)src_row_bytes : 0u));
@@ -620,8 +878,7 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
 #pragma unroll
                 for (int k = 0; k < 4; ++k) P[k] = PX::template math<LINEAR>(px[k], w[k]);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    PX::store(d + PX::kSegBytes * (k % SEGS) + (k / SEGS) * row_bytes, P[k], seg_ok[k], st, lane);
+                for (int k = 0; k < 4; ++k) PX::store(seg_ptr(d, d + row_bytes, k), P[k], seg_ok[k], st, lane);
             }
         }
         __syncthreads();  // the next item's descriptor (s_item) is complete and visible
@@ -646,15 +903,6 @@ MapCacheEntry g_map_cache[kMapCacheSize];
 unsigned long long g_map_stamp = 0;
 std::mutex g_map_mutex;
 EncodeTiledFn g_encode = nullptr;
-
-constexpr int kCounterSlots = 1024;
-unsigned char *g_flags = nullptr;  // split launches: ring of flag slices
-int g_flags_dev = -1;
-unsigned g_flag_next = 0;
-constexpr int kFlagSlices = 16, kFlagSliceBytes = 256 * 1024;
-int *g_counters = nullptr;
-int g_counters_dev = -1;
-unsigned g_counter_next = 0;
 
 // The batch viewed as a [rows][row_bytes / 4] uint32 matrix: one tensor map per box shape.
 int get_maps(const void *base, int row_bytes, long long rows, WarpFastMaps &out)
@@ -719,8 +967,19 @@ struct KernelConfig {
 // CTAs per SM the register allocation is bounded for: bilinear needs 80 registers per thread (a
 // 64-register build spills in the frame loop and is slower), nearest fits 64 without spilling and
 // gains 5 % from the fourth CTA.
-constexpr int min_ctas(bool linear) { return linear ? 3 : 4; }
-KernelConfig g_cfg[2][2][3];  // [pixel format: u8x3, f16x3][linear][tile shape: SEGS 4, 2, 1]
+#ifndef BEVK_LINEAR_CTAS
+#define BEVK_LINEAR_CTAS 3
+#endif
+constexpr int min_ctas(bool linear) { return linear ? BEVK_LINEAR_CTAS : 4; }
+// Everything that belongs to one device: the kernels' shared-memory opt-in and ring size
+// (cudaFuncSetAttribute is per device), the SM count, the memory-pool set-up.  Guarded by g_map_mutex.
+constexpr int kMaxDevices = 64;
+struct DeviceState {
+    KernelConfig cfg[2][2][3];  // [pixel format: u8x3, f16x3][linear][tile shape: SEGS 4, 2, 1]
+    int sm_count = 0;
+    bool pool_ready = false;
+};
+DeviceState g_dev[kMaxDevices];
 inline int segs_index(int segs) { return segs == 4 ? 0 : (segs == 2 ? 1 : 2); }
 
 template <typename PX, bool LINEAR, int SEGS> int configure(KernelConfig &cfg)
@@ -762,18 +1021,18 @@ template <typename PX> int configure_any(int linear, int segs, KernelConfig &cfg
 
 template <typename PX, bool LINEAR, int SEGS>
 void launch(int grid, int smem, cudaStream_t stream, const BevkWarpParams &p, const WarpFastMaps &maps,
-            const ChunkPlan &plan, int tiles_x, int tiles_y, int items, int ring_bytes, int *counter)
+            const ChunkPlan &plan, int tiles_x, int tiles_y, int items, int ring_bytes, const WarpScratch &sc)
 {
     warp_fast_kernel<PX, LINEAR, min_ctas(LINEAR), SEGS><<<grid, kThreads, smem, stream>>>(
-        p, maps, plan, tiles_x, tiles_y, items, ring_bytes, counter);
+        p, maps, plan, tiles_x, tiles_y, items, ring_bytes, sc);
 }
 template <typename PX>
 void launch_any(int linear, int segs, int grid, int smem, cudaStream_t stream, const BevkWarpParams &p,
                 const WarpFastMaps &maps, const ChunkPlan &plan, int tiles_x, int tiles_y, int items,
-                int ring_bytes, int *counter)
+                int ring_bytes, const WarpScratch &sc)
 {
 #define BEVK_LAUNCH(LIN, SEGS) \
-    launch<PX, LIN, SEGS>(grid, smem, stream, p, maps, plan, tiles_x, tiles_y, items, ring_bytes, counter)
+    launch<PX, LIN, SEGS>(grid, smem, stream, p, maps, plan, tiles_x, tiles_y, items, ring_bytes, sc)
     if (linear) {
         if (segs == 4) BEVK_LAUNCH(true, 4);
         else if (segs == 2) BEVK_LAUNCH(true, 2);
@@ -950,19 +1209,42 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
     const long long rows = (long long)n_src_frames * p.src_h;
     if (rows > 0x7fffffffLL) return 0;  // TMA coordinates are int32
 
-    // tile shape: every shape's kernel has the same ring size, so configure the widest first
-    KernelConfig &cfg0 = g_cfg[fmt][linear ? 1 : 0][0];
-    if (!cfg0.ready) {
-        int rc = fmt ? configure_any<PxF16C3>(linear, 4, cfg0) : configure_any<PxU8C3>(linear, 4, cfg0);
-        if (rc) return rc;
+    // per-device state: shared-memory opt-in + ring size of the kernels, SM count, memory pool
+    int dev = 0;
+    BEVK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) return 0;
+    DeviceState &ds = g_dev[dev];
+    KernelConfig cfg0, cfg;
+    {
+        std::lock_guard<std::mutex> lock(g_map_mutex);
+        if (!ds.sm_count) BEVK_CUDA(cudaDeviceGetAttribute(&ds.sm_count, cudaDevAttrMultiProcessorCount, dev));
+        if (!ds.pool_ready) {
+            // scratch comes from the device's default stream-ordered pool: keep what it has grown to
+            cudaMemPool_t pool;
+            BEVK_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+            unsigned long long keep_all = ~0ull;
+            BEVK_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep_all));
+            ds.pool_ready = true;
+        }
+        // tile shape: every shape's kernel has the same ring size, so configure the widest first
+        KernelConfig &c0 = ds.cfg[fmt][linear ? 1 : 0][0];
+        if (!c0.ready) {
+            int rc = fmt ? configure_any<PxF16C3>(linear, 4, c0) : configure_any<PxU8C3>(linear, 4, c0);
+            if (rc) return rc;
+        }
+        cfg0 = c0;
     }
     bool split = false;
     const int segs = pick_tile_shape(p, linear, bpp, cfg0.ring_bytes, force != 0, &split);
     if (segs == 0) return 0;
-    KernelConfig &cfg = g_cfg[fmt][linear ? 1 : 0][segs_index(segs)];
-    if (!cfg.ready) {
-        int rc = fmt ? configure_any<PxF16C3>(linear, segs, cfg) : configure_any<PxU8C3>(linear, segs, cfg);
-        if (rc) return rc;
+    {
+        std::lock_guard<std::mutex> lock(g_map_mutex);
+        KernelConfig &c = ds.cfg[fmt][linear ? 1 : 0][segs_index(segs)];
+        if (!c.ready) {
+            int rc = fmt ? configure_any<PxF16C3>(linear, segs, c) : configure_any<PxU8C3>(linear, segs, c);
+            if (rc) return rc;
+        }
+        cfg = c;
     }
 
     WarpFastMaps maps;
@@ -972,12 +1254,12 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
     const int tiles_x = (p.dst_w + tile_w(segs) - 1) / tile_w(segs);
     const int tiles_y = (p.dst_h + tile_h(segs) - 1) / tile_h(segs);
     const long long n_tiles = (long long)tiles_x * tiles_y;
-    const int ctas = bevk_sm_count() * cfg.ctas_per_sm;
+    const int ctas = ds.sm_count * cfg.ctas_per_sm;
 
-    // Frame chunks.  Every (tile, chunk) item pays one FP64 set-up, so chunks should be long; the
-    // CTAs pull items from a shared counter, so the LAST items should be short.  With enough
-    // frames the chunk lengths therefore decay (5/16, 4/16, 3/16, 1/8, then ever smaller);
-    // short batches get fewer, equal chunks, just enough for ~3 items per CTA.
+    // Frame chunks.  The CTAs pull (tile, chunk) items from a shared counter, so the LAST items
+    // should be short: with enough frames the chunk lengths decay (5/16, 4/16, 3/16, 1/8, then
+    // ever smaller).  The FP64 set-up of a tile is computed by its first chunk and re-read by the
+    // others (WarpScratch).  Short batches get fewer, equal chunks, just enough for ~3 items per CTA.
     ChunkPlan plan;
     memset(&plan, 0, sizeof(plan));
     const long long tile_groups = n_tiles * p.n_groups;
@@ -998,58 +1280,77 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
     if (items > 0x7fffffffLL) return 0;
     const int grid = (int)(items < ctas ? items : ctas);
 
-    // shared item counter: one zeroed slot per launch out of a ring (launches on different
-    // streams may overlap).  Not needed when every CTA has exactly one item.
-    int *counter = nullptr;
-    if (items > grid) {
-        std::lock_guard<std::mutex> lock(g_map_mutex);
-        int dev = 0;
-        BEVK_CUDA(cudaGetDevice(&dev));
-        if (!g_counters || g_counters_dev != dev) {
-            if (g_counters) cudaFree(g_counters);
-            g_counters = nullptr;
-            BEVK_CUDA(cudaMalloc(&g_counters, kCounterSlots * sizeof(int)));
-            g_counters_dev = dev;
+    // Per-launch scratch, allocated and freed in stream order (launches on other streams or from
+    // other threads get their own): [item counter | split flags | set-up ready flags] zeroed, then
+    // the tiles' set-up headers and records.
+    split = split && !getenv("BEVK_NO_SPLIT");  // env: tuning aid
+    const bool share_setup = plan.n_chunks > 1 && tile_groups * kRecWords * kThreads * 4 <= (512LL << 20) &&
+                             !getenv("BEVK_NO_SETUP_CACHE");
+    const size_t off_hard = 256;
+    const size_t off_ready = off_hard + (((size_t)(split ? tile_groups : 0) + 255) & ~(size_t)255);
+    const size_t off_hdr = off_ready + (((size_t)(share_setup ? tile_groups * 4 : 0) + 255) & ~(size_t)255);
+    const size_t off_rec = off_hdr + (share_setup ? (size_t)tile_groups * kHdrInts * 4 : 0);
+    const size_t total = off_rec + (share_setup ? (size_t)tile_groups * kRecWords * kThreads * 4 : 0);
+    unsigned char *scratch = nullptr;
+    BEVK_CUDA(cudaMallocAsync((void **)&scratch, total, stream));
+    cudaError_t e = cudaMemsetAsync(scratch, 0, off_hdr, stream);
+    WarpScratch sc;
+    sc.next_item = (int *)scratch;
+    sc.ready = share_setup ? (int *)(scratch + off_ready) : nullptr;
+    sc.hdr = share_setup ? (int *)(scratch + off_hdr) : nullptr;
+    sc.rec = share_setup ? (uint32_t *)(scratch + off_rec) : nullptr;
+    sc.no_pairs = getenv("BEVK_NO_PAIRS") ? 1 : 0;
+    sc.dbg = getenv("BEVK_DBG") ? atoi(getenv("BEVK_DBG")) : 0;
+    sc.slack = getenv("BEVK_SLACK") ? atoi(getenv("BEVK_SLACK")) : 0;
+    sc.pf = getenv("BEVK_PF") ? atoi(getenv("BEVK_PF")) : -1;
+    sc.max_fps = getenv("BEVK_MAXFPS") ? atoi(getenv("BEVK_MAXFPS")) : kMaxStageFrames;
+    {
+        // stride permutation of the tile rows: groups of y_group adjacent rows stay together (their
+        // source boxes overlap and are re-served by L2), the groups are visited ~3/8 of a column apart
+        int g = getenv("BEVK_YGROUP") ? atoi(getenv("BEVK_YGROUP")) : 0;
+        if (g < 1 || tiles_y % g != 0) g = 0;
+        sc.y_group = g ? g : 1;
+        const int n = tiles_y / sc.y_group;
+        int st = 1;
+        if (g) {
+            st = (3 * n) / 8;
+            if (st < 1) st = 1;
+            auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
+            while (gcd(st, n) != 1) ++st;
         }
-        counter = g_counters + (g_counter_next++ % kCounterSlots);
+        sc.y_stride = st;
     }
-    if (counter) BEVK_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));
-
-    // split launch: one byte per (group, tile), a zeroed slice of a ring of flag buffers
-    const long long n_flags = n_tiles * p.n_groups;
-    split = split && n_flags <= kFlagSliceBytes && !getenv("BEVK_NO_SPLIT");  // env: tuning aid
     if (split) {
-        std::lock_guard<std::mutex> lock(g_map_mutex);
-        int dev = 0;
-        BEVK_CUDA(cudaGetDevice(&dev));
-        if (!g_flags || g_flags_dev != dev) {
-            if (g_flags) cudaFree(g_flags);
-            g_flags = nullptr;
-            BEVK_CUDA(cudaMalloc(&g_flags, (size_t)kFlagSlices * kFlagSliceBytes));
-            g_flags_dev = dev;
-        }
-        p.hard = g_flags + (size_t)(g_flag_next++ % kFlagSlices) * kFlagSliceBytes;
+        // one byte per (group, tile): the staged kernel marks the tiles it leaves to the second launch
+        p.hard = scratch + off_hard;
         p.hard_tw = tile_w(segs);
         p.hard_th = tile_h(segs);
         p.hard_ty = tiles_y;
         p.hard_tiles = (int)n_tiles;
-        BEVK_CUDA(cudaMemsetAsync(p.hard, 0, (size_t)n_flags, stream));
     }
 
-    const int smem = cfg.ring_bytes + kBarBytes + kTailSlack;
-    if (fmt)
-        launch_any<PxF16C3>(linear, segs, grid, smem, stream, p, maps, plan, tiles_x, tiles_y, (int)items,
-                            cfg.ring_bytes, counter);
-    else
-        launch_any<PxU8C3>(linear, segs, grid, smem, stream, p, maps, plan, tiles_x, tiles_y, (int)items,
-                           cfg.ring_bytes, counter);
-    BEVK_CUDA(cudaGetLastError());
-    if (split) {
-        // the tiles the staged kernel marked, through the direct-gather kernel (same stream)
-        int rc2 = bevk_plan_generic_chunks(p, channels);
-        if (rc2) return rc2;
-        rc2 = bevk_launch_warp_generic(p, channels, dtype, linear, stream);
-        if (rc2) return rc2;
+    int rc2 = 0;
+    if (e == cudaSuccess) {
+        const int smem = cfg.ring_bytes + kBarBytes + kTailSlack;
+        if (fmt)
+            launch_any<PxF16C3>(linear, segs, grid, smem, stream, p, maps, plan, tiles_x, tiles_y, (int)items,
+                                cfg.ring_bytes, sc);
+        else
+            launch_any<PxU8C3>(linear, segs, grid, smem, stream, p, maps, plan, tiles_x, tiles_y, (int)items,
+                               cfg.ring_bytes, sc);
+        e = cudaGetLastError();
+        if (e == cudaSuccess && split) {
+            // the tiles the staged kernel marked, through the direct-gather kernel (same stream)
+            rc2 = bevk_plan_generic_chunks(p, channels);
+            if (!rc2) rc2 = bevk_launch_warp_generic(p, channels, dtype, linear, stream);
+        }
     }
+    const cudaError_t ef = cudaFreeAsync(scratch, stream);  // stream-ordered: after the kernels above
+    if (e != cudaSuccess) {
+        bevk_set_error("staged warp launch failed: %s", cudaGetErrorString(e));
+        return BEVK_E_CUDA;
+    }
+    if (rc2) return rc2;
+    BEVK_CUDA(ef);
     return 1;
 }

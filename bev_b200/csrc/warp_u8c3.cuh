@@ -55,20 +55,28 @@ __device__ __forceinline__ uint32_t tap_weight(int wc, int wr)
     return min((uint32_t)(wc * wr) * 64u, 65535u);
 }
 
-// One pixel out of its staged window: cv2's fixed-point bilinear, result [c0, c1, c2, 0].
-// f0 / g0 = window bytes 0..3 of row 0 / 1, f1 / g1 = window bytes 4.. (already byte-aligned).
-// Per row the channel pairs are gathered into [B0 B3 B1 B4] and [B2 B5 . .]; every channel is then
-// two chained dp2a (row 0, row 1) starting from the rounding constant -- no multiplies.
+// cv2's fixed-point bilinear from gathered taps.  Per window row the channel pairs are gathered
+// into xa = [B0 B3 B1 B4], ya = [B2 B5 . .] (row 0) and xb, yb (row 1), B0..B5 being the six bytes
+// of the row's two pixels; every channel is then two chained dp2a (row 0, row 1) starting from the
+// rounding constant -- no multiplies.  w0 / w1 = the two tap weights of row 0 / 1 as 16-bit halves.
+// Result [c0, c1, c2, 0].
+__device__ __forceinline__ uint32_t lerp_xy(uint32_t w0, uint32_t w1, uint32_t xa, uint32_t ya, uint32_t xb,
+                                            uint32_t yb)
+{
+    const uint32_t t0 = __dp2a_lo(w1, xb, __dp2a_lo(w0, xa, 32768u));
+    const uint32_t t1 = __dp2a_hi(w1, xb, __dp2a_hi(w0, xa, 32768u));
+    const uint32_t t2 = __dp2a_lo(w1, yb, __dp2a_lo(w0, ya, 32768u));
+    // byte 2 of t is (sum w*p + 2^14) >> 15 in cv2's scale
+    return prmt(prmt(t0, t1, 0x4462u), t2, 0x7610u);
+}
+
+// One pixel out of its staged window.  f0 / g0 = window bytes 0..3 of row 0 / 1, f1 / g1 = window
+// bytes 4.. (already byte-aligned).
 __device__ __forceinline__ uint32_t lerp_aligned(const Pix &q, uint32_t f0, uint32_t f1, uint32_t g0,
                                                  uint32_t g1)
 {
-    const uint32_t xa = prmt(f0, f1, 0x4130u), ya = prmt(f0, f1, 0x0052u);
-    const uint32_t xb = prmt(g0, g1, 0x4130u), yb = prmt(g0, g1, 0x0052u);
-    const uint32_t t0 = __dp2a_lo(q.w1, xb, __dp2a_lo(q.w0, xa, 32768u));
-    const uint32_t t1 = __dp2a_hi(q.w1, xb, __dp2a_hi(q.w0, xa, 32768u));
-    const uint32_t t2 = __dp2a_lo(q.w1, yb, __dp2a_lo(q.w0, ya, 32768u));
-    // byte 2 of t is (sum w*p + 2^14) >> 15 in cv2's scale
-    return prmt(prmt(t0, t1, 0x4462u), t2, 0x7610u);
+    return lerp_xy(q.w0, q.w1, prmt(f0, f1, 0x4130u), prmt(f0, f1, 0x0052u), prmt(g0, g1, 0x4130u),
+                   prmt(g0, g1, 0x0052u));
 }
 
 
@@ -79,6 +87,7 @@ struct PxU8C3 {
     static constexpr int kBpp = 3;         // bytes per pixel
     static constexpr int kSegBytes = 96;   // bytes of a 32-pixel row segment
     static constexpr int kDtype = BEVK_U8;
+    static constexpr bool kPairs = true;   // the staged kernel's shared-window pair path exists for this format
     using Reg = Pix;
     using Out = uint32_t;                  // [c0, c1, c2, 0]
     struct Store {
@@ -101,6 +110,20 @@ struct PxU8C3 {
             q.w1 = 0;
         }
         return q;
+    }
+    // the same from the packed integer weights wc0 | wc1 << 8 | wr0 << 16 | wr1 << 24 (0 = inactive)
+    template <bool LINEAR> static __device__ __forceinline__ Reg make(bool act, uint32_t A, uint32_t wpk)
+    {
+        return make<LINEAR>(act, A, (int)(wpk & 0xffu), (int)((wpk >> 8) & 0xffu), (int)((wpk >> 16) & 0xffu),
+                            (int)(wpk >> 24));
+    }
+    // dp2a operands of window rows 0 / 1 from the packed integer weights
+    static __device__ __forceinline__ void tap_weights(uint32_t wpk, uint32_t &w0, uint32_t &w1)
+    {
+        const int wc0 = (int)(wpk & 0xffu), wc1 = (int)((wpk >> 8) & 0xffu);
+        const int wr0 = (int)((wpk >> 16) & 0xffu), wr1 = (int)(wpk >> 24);
+        w0 = tap_weight(wc0, wr0) | (tap_weight(wc1, wr0) << 16);
+        w1 = tap_weight(wc0, wr1) | (tap_weight(wc1, wr1) << 16);
     }
     // window words per row that are always needed / offset of the last one, which only some
     // alignments need (the direct-gather fallback clamps that one into the frame)
