@@ -140,6 +140,24 @@ def _require_cuda(t, what):
                            "fallback" % (what, t.device))
 
 
+def _aligned(t, align=4):
+    """Contiguous tensor whose data pointer is `align`-byte aligned (a contiguous VIEW at an odd
+    byte offset -- e.g. the second half of a concatenated uint8 batch -- is copied)."""
+    t = t.contiguous()
+    if t.data_ptr() % align:
+        t = t.clone()
+    return t
+
+
+def _check_out(out, like, what):
+    """`out` must be a contiguous tensor of `like`'s shape, dtype and device."""
+    _require_cuda(out, what)
+    if tuple(out.shape) != tuple(like.shape) or out.dtype != like.dtype or out.device != like.device \
+            or not out.is_contiguous():
+        raise ValueError("%s must be a contiguous %s tensor of shape %s on %s"
+                         % (what, like.dtype, tuple(like.shape), like.device))
+
+
 def _warp_dtype(t):
     import torch
     code = {torch.uint8: U8, torch.float16: F16, torch.float32: F32}.get(t.dtype)
@@ -322,11 +340,15 @@ def resize(src, dsize, interpolation=1, dst=None):
     elif src.dim() == 3:
         s4 = s4[None]
     n, sh, sw, c = s4.shape
+    want = {2: (h, w), 3: (h, w, c), 4: (n, h, w, c)}[src.dim()]
     if dst is None:
         dst = torch.empty((n, h, w, c), dtype=torch.uint8, device=src.device)
-    elif tuple(dst.shape[-3:] if src.dim() != 2 else dst.shape[-2:]) != ((h, w, c) if src.dim() != 2 else (h, w)) \
-            or dst.dtype != torch.uint8 or not dst.is_contiguous() or dst.device != src.device:
-        raise ValueError("resize: dst must be a contiguous uint8 tensor of the output shape on src's device")
+    else:
+        _require_cuda(dst, "dst")
+        if tuple(dst.shape) != want or dst.dtype != torch.uint8 or not dst.is_contiguous() \
+                or dst.device != src.device:
+            raise ValueError("resize: dst must be a contiguous uint8 tensor of shape %s on %s, got %s %s on %s"
+                             % (want, src.device, dst.dtype, tuple(dst.shape), dst.device))
     with torch.cuda.device(src.device):
         rc = lib().bevk_resize(_vp(s4.data_ptr()), _vp(dst.data_ptr()), n, sh, sw, h, w, c, 0,
                                int(interpolation), _stream_ptr(src))
@@ -349,9 +371,18 @@ def composite_u8c3(bg, fg, fg_mask, bw_mode=False, out=None):
     if not (tuple(bg.shape) == tuple(fg.shape) == tuple(fg_mask.shape)) or bg.shape[-1] != 3:
         raise ValueError("bg, fg and fg_mask must share one (..., 3) shape; got %s %s %s"
                          % (tuple(bg.shape), tuple(fg.shape), tuple(fg_mask.shape)))
-    bg, fg, fg_mask = bg.contiguous(), fg.contiguous(), fg_mask.contiguous()
+    if not (bg.device == fg.device == fg_mask.device):
+        raise ValueError("bg, fg and fg_mask must be on one device; got %s %s %s"
+                         % (bg.device, fg.device, fg_mask.device))
+    # the kernel reads 4-byte words: views at an odd byte offset (the mask half of a concatenated
+    # warp output, user slices) are realigned by a copy
+    bg, fg, fg_mask = _aligned(bg), _aligned(fg), _aligned(fg_mask)
     if out is None:
         out = torch.empty_like(bg)
+    else:
+        _check_out(out, bg, "out")
+        if out.data_ptr() % 4:
+            raise ValueError("out must be 4-byte aligned")
     n_pixels = bg.numel() // 3
     with torch.cuda.device(bg.device):
         rc = lib().bevk_composite_u8c3(_vp(bg.data_ptr()), _vp(fg.data_ptr()), _vp(fg_mask.data_ptr()),
@@ -387,10 +418,19 @@ def composite_bev_u8c3(bg, fg, fg_mask, H_bg, H_fg, dsize, out=None):
     Hf = np.ascontiguousarray(np.asarray(_to_numpy(H_fg), np.float64).reshape(-1, 9))
     if Hb.shape[0] != Hf.shape[0] or Hb.shape[0] not in (1, n):
         raise ValueError("need 1 or %d homography pairs, got %d / %d" % (n, Hb.shape[0], Hf.shape[0]))
-    bg, fg, fg_mask = bg.contiguous(), fg.contiguous(), fg_mask.contiguous()
+    if not (bg.device == fg.device == fg_mask.device):
+        raise ValueError("bg, fg and fg_mask must be on one device; got %s %s %s"
+                         % (bg.device, fg.device, fg_mask.device))
+    bg, fg, fg_mask = _aligned(bg, 16), _aligned(fg, 16), _aligned(fg_mask, 16)
     w, h = int(dsize[0]), int(dsize[1])
     if out is None:
         out = torch.empty((n, h, w, 3), dtype=torch.uint8, device=fg.device)
+    else:
+        _require_cuda(out, "out")
+        if tuple(out.shape) != (n, h, w, 3) or out.dtype != torch.uint8 or not out.is_contiguous() \
+                or out.device != fg.device or out.data_ptr() % 4:
+            raise ValueError("out must be a contiguous, 4-byte aligned uint8 tensor of shape %s on %s"
+                             % ((n, h, w, 3), fg.device))
     with torch.cuda.device(fg.device):
         rc = lib().bevk_composite_bev_u8c3(
             _vp(bg.data_ptr()), _vp(fg.data_ptr()), _vp(fg_mask.data_ptr()), _vp(out.data_ptr()),

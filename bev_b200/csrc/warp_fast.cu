@@ -69,6 +69,11 @@ constexpr int kMaxBoxes = 3;
 constexpr int kMaxStageFrames = 4;              // frames that share one ring stage / mbarrier phase
 constexpr int kBarBytes = 256;                  // 28 mbarriers: ring depths 2, 4 and 8
 constexpr int kPrefetchAhead = 2;               // depth-2 rings: L2 prefetch runs this many stages ahead
+#ifdef BEVK_EXPERIMENTS
+constexpr bool kExperiments = true;   // build with -DBEVK_EXPERIMENTS: the BEVK_DBG ablation switches exist
+#else
+constexpr bool kExperiments = false;
+#endif
 constexpr int kTailSlack = 64;                  // window words may run a few bytes past a stage
 
 __host__ __device__ constexpr int map_width(int wi)
@@ -126,10 +131,12 @@ struct WarpScratch {
     int *hdr;         // [groups * tiles][kHdrInts]
     uint32_t *rec;    // [groups * tiles][kRecWords][kThreads]
     int no_pairs;     // tuning aid (BEVK_NO_PAIRS): every warp takes the per-pixel path
-    int dbg;          // experiments (BEVK_DBG): 1 = no stores, 2 = no TMA traffic / waits (results are garbage)
+    int dbg;          // -DBEVK_EXPERIMENTS builds only (BEVK_DBG): 1 = no stores, 2 = no TMA traffic / waits
     int slack;        // ring stages NOT in flight ahead of the consumers (0: half the ring)
     int pf;           // L2 prefetch distance in stages beyond the fills (-1: depth-2 rings only, 2 stages)
+    int pf1;          // the same for depth-2 rings when pf < 0
     int max_fps;      // frames per ring stage, at most
+    int row_major;    // walk the tiles row by row instead of column by column
     int y_group, y_stride;  // tile rows are walked in groups of y_group, group g at (g * y_stride) % n_groups
 };
 
@@ -225,6 +232,7 @@ struct ItemDesc {
     int f0, n_frames;         // frames [f0, f0 + n_frames) of the group's run
     int first, stride;        // the run: frame index = first + f * stride
     int chunk;                // frame chunk; chunk 0 computes (and publishes) the tile's set-up
+    int ready;                // chunk > 0: the tile's set-up was already published when the item was decoded
 };
 
 // The consumers' loop state (kept small so that the frame loop fits its register budget); the
@@ -307,7 +315,7 @@ __device__ __forceinline__ uint32_t stage_loop(const LoopCtx &c, uint32_t use, u
 {
     const uint32_t smask = (1u << c.slog) - 1u;
     const int lane = tid & 31, warp = tid >> 5;
-    if (tid == 0 && !(c.dbg & 2)) {
+    if (tid == 0 && !(kExperiments && (c.dbg & 2))) {
         for (int s = 0; s < c.ahead && s * c.fps < c.n_frames; ++s)
             produce<true>(c.plan, c.maps, s * c.fps, use + s);
         for (int s = c.ahead; s < c.ahead + c.pf && s * c.fps < c.n_frames; ++s)
@@ -318,14 +326,14 @@ __device__ __forceinline__ uint32_t stage_loop(const LoopCtx &c, uint32_t use, u
     while (done < c.n_frames) {
         const uint32_t slot = use & smask;
         const uint32_t fb = c.full0 + 8 * slot;
-        if (!(c.dbg & 2)) mbar_wait(fb, (use >> c.slog) & 1u);
+        if (!(kExperiments && (c.dbg & 2))) mbar_wait(fb, (use >> c.slog) & 1u);
         uint32_t sa = c.ring + slot * c.stride;  // first frame of the stage
         int nf = min(c.fps, c.n_frames - done);
         done += nf;
 #pragma unroll 1
         for (; nf > 0; --nf, sa += c.frame_bytes, d += d_step) {
             body(sa, d, [&]() {
-                if (nf == 1 && !(c.dbg & 2)) {
+                if (nf == 1 && !(kExperiments && (c.dbg & 2))) {
                     // every shared-memory read of this stage is issued: hand the slot back
                     __syncwarp();
                     if (lane == 0) mbar_arrive(fb + (8u << c.slog));
@@ -366,35 +374,60 @@ template <int SEGS> __device__ __forceinline__ constexpr int px_row(int k) { ret
 // starts 0 or 3 bytes into it.
 struct PairReg {
     uint32_t addr;         // byte offset (4-aligned) inside a staged frame of the span, first row
-    uint32_t sh, shv;      // funnel-shift amounts: 8 * (start & 3), 8 * ((start + 2) & 3)
-    uint32_t sel_f, sel_s; // PRMT selector of the first / second pixel: window at byte 0 or 3
+    uint32_t sh;           // funnel-shift amount that byte-aligns the span: 8 * (start & 3)
+    uint32_t sel_f, sel_s; // PRMT selector of the first / second pixel: window at span byte 0 or 3
+    uint32_t sel_y;        // PRMT selector that gathers the third channel's taps of both pixels
     uint32_t wf0, wf1;     // dp2a tap weights of the first pixel, its window rows 0 / 1
     uint32_t ws0, ws1;     // ... of the second pixel
 };
 
-// One staged row of a pair's span: byte-align it (g0 = bytes 0..3, g1 = 4..7) and put the bytes
-// the third channel of either window needs where one selector serves both PRMTs:
-//   window at byte 0 (selector 0x4130): xa = [b0 b3 b1 b4]  ya = [b2 b5 . .]
-//   window at byte 3 (selector 0x7463): xa = [b3 b6 b4 b7]  ya = [b5 b8 . .]
-// with ya = prmt(u, v, sel), u = [b2 . . b5], v = [. . b8 .].
+// One staged row of a pair's span, byte-aligned: g0 = span bytes 0..3, g1 = 4..7, and the pool
+// (u, w2) that holds the third-channel taps b2, b5 (u = [b2 . . b5]) and b8 (byte `start & 3` of
+// the raw word w2).  A window at span byte 0 / 3 is gathered as
+//   xa = prmt(g0, g1, 0x4130 / 0x7463) = [b0 b3 b1 b4] / [b3 b6 b4 b7]   (channels 0, 1: two taps each)
+//   y  = prmt(u, w2, sel_y)            = [c2 taps of the first pixel | c2 taps of the second]
 struct PairRow {
-    uint32_t g0, g1, u, v;
+    uint32_t g0, g1, u, w2;
 };
-__device__ __forceinline__ PairRow pair_row(uint32_t a, uint32_t sh, uint32_t shv)
+__device__ __forceinline__ PairRow pair_row(uint32_t a, uint32_t sh)
 {
-    const uint32_t w0 = lds32(a), w1 = lds32(a + 4), w2 = lds32(a + 8);
+    const uint32_t w0 = lds32(a), w1 = lds32(a + 4);
     PairRow r;
+    r.w2 = lds32(a + 8);
     r.g0 = __funnelshift_r(w0, w1, sh);
-    r.g1 = __funnelshift_r(w1, w2, sh);
-    r.v = __funnelshift_r(w2, w2, shv);  // byte 2 = span byte 8
+    r.g1 = __funnelshift_r(w1, r.w2, sh);
     r.u = prmt(r.g0, r.g1, 0x5002u);
     return r;
 }
-__device__ __forceinline__ uint32_t pair_lerp(const PairRow &r0, const PairRow &r1, uint32_t sel, uint32_t w0,
-                                              uint32_t w1)
+// sel_y for window offsets df, ds (0 or 1 pixel into the span) and span start byte o = start & 3
+__device__ __forceinline__ uint32_t pair_sel_y(bool df, bool ds, uint32_t o)
 {
-    return lerp_xy(w0, w1, prmt(r0.g0, r0.g1, sel), prmt(r0.u, r0.v, sel), prmt(r1.g0, r1.g1, sel),
-                   prmt(r1.u, r1.v, sel));
+    const uint32_t f = df ? (3u | ((4u + o) << 4)) : (0u | (3u << 4));
+    const uint32_t s2 = ds ? (3u | ((4u + o) << 4)) : (0u | (3u << 4));
+    return f | (s2 << 8);
+}
+// cv2's fixed-point bilinear of the pair's two pixels: rows (a0, a1) hold the first pixel's window,
+// (b0, b1) the second's (the same two rows in the 2-row variant).  ya* / yb* = the y gathers of
+// those rows.  Results [c0 c1 c2 0].
+__device__ __forceinline__ void pair_lerp(const PairReg &q, const PairRow &a0, const PairRow &a1,
+                                          const PairRow &b0, const PairRow &b1, uint32_t ya0, uint32_t ya1,
+                                          uint32_t yb0, uint32_t yb1, uint32_t &pf, uint32_t &ps)
+{
+    const uint32_t rnd = 32768u;
+    {
+        const uint32_t x0 = prmt(a0.g0, a0.g1, q.sel_f), x1 = prmt(a1.g0, a1.g1, q.sel_f);
+        const uint32_t t0 = __dp2a_lo(q.wf1, x1, __dp2a_lo(q.wf0, x0, rnd));
+        const uint32_t t1 = __dp2a_hi(q.wf1, x1, __dp2a_hi(q.wf0, x0, rnd));
+        const uint32_t t2 = __dp2a_lo(q.wf1, ya1, __dp2a_lo(q.wf0, ya0, rnd));
+        pf = prmt(prmt(t0, t1, 0x4462u), t2, 0x7610u);
+    }
+    {
+        const uint32_t x0 = prmt(b0.g0, b0.g1, q.sel_s), x1 = prmt(b1.g0, b1.g1, q.sel_s);
+        const uint32_t t0 = __dp2a_lo(q.ws1, x1, __dp2a_lo(q.ws0, x0, rnd));
+        const uint32_t t1 = __dp2a_hi(q.ws1, x1, __dp2a_hi(q.ws0, x0, rnd));
+        const uint32_t t2 = __dp2a_hi(q.ws1, yb1, __dp2a_hi(q.ws0, yb0, rnd));
+        ps = prmt(prmt(t0, t1, 0x4462u), t2, 0x7610u);
+    }
 }
 
 // MINB = CTAs per SM the register allocation is bounded for (4 -> 64 registers, 3 -> 80);
@@ -454,8 +487,14 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
         // column-major walk: concurrently running CTAs cover whole tile columns, i.e. both the
         // magnified far field (store-heavy) and the minified near field (load-heavy)
         o.gi = gi;
-        o.tile_x = tile / tiles_y;
-        const int ty = tile - o.tile_x * tiles_y;
+        int ty;
+        if (sc.row_major) {
+            ty = tile / tiles_x;
+            o.tile_x = tile - ty * tiles_x;
+        } else {
+            o.tile_x = tile / tiles_y;
+            ty = tile - o.tile_x * tiles_y;
+        }
         // ... with the tile rows of a column permuted by a stride, so that the CTAs that share an
         // SM (consecutive items) work on different zones of the map at any time
         const int yg = ty / sc.y_group;
@@ -466,6 +505,10 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
         o.first = p.g[gi].first;
         o.stride = p.g[gi].stride;
         o.chunk = chunk;
+        // one item ahead of its use: by then the first chunk's CTA has nearly always published
+        o.ready = (sc.ready != nullptr && chunk > 0)
+                      ? ld_acquire(sc.ready + (gi * n_tiles + o.tile_x * tiles_y + o.tile_y))
+                      : 1;
     };
     for (int i = tid; i < p.n_groups * 9; i += kThreads) s_M[i / 9][i % 9] = p.g[i / 9].M[i % 9];
     if (tid == 0) {
@@ -487,6 +530,7 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
         const int f0 = s_item[par].f0, n_frames = s_item[par].n_frames;
         const int g_first = s_item[par].first, g_stride = s_item[par].stride;
         const int chunk = s_item[par].chunk;
+        const bool published = s_item[par].ready != 0;
         const int x0 = tile_x * tile_w(SEGS) + warp_px_x<SEGS>(warp);
         const int y0 = tile_y * tile_h(SEGS) + warp_px_y<SEGS>(warp);
         const int tile_id = gi * n_tiles + tile_x * tiles_y + tile_y;
@@ -562,9 +606,11 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
                 __threadfence();  // ordered before the release store that follows the next barrier
             }
         } else {
-            if (tid == 0) {
-                const int *flag = sc.ready + tile_id;
-                while (ld_acquire(flag) == 0) __nanosleep(100);
+            if (!published) {  // rare: wait for the CTA that runs the tile's first chunk
+                if (tid == 0) {
+                    const int *flag = sc.ready + tile_id;
+                    while (ld_acquire(flag) == 0) __nanosleep(100);
+                }
             }
             __syncthreads();
             const int4 *h = reinterpret_cast<const int4 *>(sc.hdr + (size_t)tile_id * kHdrInts);
@@ -669,7 +715,7 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
             if (SEGS >= 2) return (px_row<SEGS>(k) ? dd1 : dd) + PX::kSegBytes * px_seg<SEGS>(k);
             return (k & 1 ? dd1 : dd) + (k >> 1) * 2 * (size_t)row_bytes;
         };
-        if (sc.dbg & 1) seg_ok[0] = seg_ok[1] = seg_ok[2] = seg_ok[3] = false;
+        if (kExperiments && (sc.dbg & 1)) seg_ok[0] = seg_ok[1] = seg_ok[2] = seg_ok[3] = false;
         uint32_t d_step = (uint32_t)g_stride * (uint32_t)dst_frame_bytes;  // < 2^32 (host check)
         keep(d_step);
         uint8_t *d = dst + (long long)(g_first + f0 * g_stride) * dst_frame_bytes +
@@ -692,7 +738,7 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
             c.n_frames = n_frames;
             c.slog = slog;
             c.ahead = sc.slack ? max(1, (1 << slog) - sc.slack) : (1 << (slog - 1));
-            c.pf = sc.pf >= 0 ? sc.pf : (slog == 1 ? kPrefetchAhead : 0);
+            c.pf = sc.pf >= 0 ? sc.pf : (slog == 1 ? sc.pf1 : 0);
             c.dbg = sc.dbg;
             c.maps = &maps;
             c.plan = &s_plan;
@@ -751,14 +797,14 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
                     const uint32_t A = (uint32_t)((rf - by0) * pitch + kBpp * c0 - a0);
                     pr[j].addr = A & ~3u;
                     pr[j].sh = 8 * (A & 3);
-                    pr[j].shv = 8 * ((A + 2) & 3);
                     pr[j].sel_f = cf != c0 ? 0x7463u : 0x4130u;
                     pr[j].sel_s = cn != c0 ? 0x7463u : 0x4130u;
+                    pr[j].sel_y = pair_sel_y(cf != c0, cn != c0, A & 3);
                     PxU8C3::tap_weights(wp_f, pr[j].wf0, pr[j].wf1);
                     PxU8C3::tap_weights(wp_s, pr[j].ws0, pr[j].ws1);
                     keep(pr[j].addr);
                     keep(pr[j].sh);
-                    keep(pr[j].shv);
+                    keep(pr[j].sel_y);
                     keep(pr[j].sel_f);
                     keep(pr[j].sel_s);
                     ok |= ((sw ? seg_ok[2 * j + 1] : seg_ok[2 * j]) ? 1u : 0u) << (2 * j);
@@ -773,11 +819,11 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
                         uint32_t P[4];
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
-                            const PairRow r0 = pair_row(pr[j].addr + sa, pr[j].sh, pr[j].shv);
-                            const PairRow r1 = pair_row(pr[j].addr + sb, pr[j].sh, pr[j].shv);
+                            const PairRow r0 = pair_row(pr[j].addr + sa, pr[j].sh);
+                            const PairRow r1 = pair_row(pr[j].addr + sb, pr[j].sh);
                             if (j == 1) release();
-                            P[2 * j] = pair_lerp(r0, r1, pr[j].sel_f, pr[j].wf0, pr[j].wf1);
-                            P[2 * j + 1] = pair_lerp(r0, r1, pr[j].sel_s, pr[j].ws0, pr[j].ws1);
+                            const uint32_t y0 = prmt(r0.u, r0.w2, pr[j].sel_y), y1 = prmt(r1.u, r1.w2, pr[j].sel_y);
+                            pair_lerp(pr[j], r0, r1, r0, r1, y0, y1, y0, y1, P[2 * j], P[2 * j + 1]);
                         }
                         // dd points into the first pixels' dst row, the second pixels' is one row on / back
                         uint8_t *ds = dd + d_second;
@@ -793,12 +839,13 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
                         uint32_t P[4];
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
-                            const PairRow r0 = pair_row(pr[j].addr + sa, pr[j].sh, pr[j].shv);
-                            const PairRow r1 = pair_row(pr[j].addr + sb, pr[j].sh, pr[j].shv);
-                            const PairRow r2 = pair_row(pr[j].addr + sc2, pr[j].sh, pr[j].shv);
+                            const PairRow r0 = pair_row(pr[j].addr + sa, pr[j].sh);
+                            const PairRow r1 = pair_row(pr[j].addr + sb, pr[j].sh);
+                            const PairRow r2 = pair_row(pr[j].addr + sc2, pr[j].sh);
                             if (j == 1) release();
-                            P[2 * j] = pair_lerp(r0, r1, pr[j].sel_f, pr[j].wf0, pr[j].wf1);
-                            P[2 * j + 1] = pair_lerp(r1, r2, pr[j].sel_s, pr[j].ws0, pr[j].ws1);
+                            const uint32_t y0 = prmt(r0.u, r0.w2, pr[j].sel_y), y1 = prmt(r1.u, r1.w2, pr[j].sel_y);
+                            const uint32_t y2 = prmt(r2.u, r2.w2, pr[j].sel_y);
+                            pair_lerp(pr[j], r0, r1, r1, r2, y0, y1, y1, y2, P[2 * j], P[2 * j + 1]);
                         }
                         // dd points into the first pixels' dst row, the second pixels' is one row on / back
                         uint8_t *ds = dd + d_second;
@@ -1263,7 +1310,17 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
     ChunkPlan plan;
     memset(&plan, 0, sizeof(plan));
     const long long tile_groups = n_tiles * p.n_groups;
-    if (max_count >= 128 && tile_groups * 5 >= 2LL * ctas) {
+    if (const char *env = getenv("BEVK_CHUNKS")) {  // tuning aid: chunk lengths in 1/256ths, e.g. "96,64,48,32,16"
+        int k = 0, acc = 0;
+        for (const char *q = env; *q && k < kMaxChunks;) {
+            acc += atoi(q);
+            plan.cum[++k] = (uint32_t)(acc * 256);
+            while (*q && *q != ',') ++q;
+            if (*q == ',') ++q;
+        }
+        plan.cum[k] = 65536;
+        plan.n_chunks = k;
+    } else if (max_count >= 128 && tile_groups * 5 >= 2LL * ctas) {
         static const uint32_t cum[8] = {0, 20480, 36864, 49152, 57344, 61952, 64512, 65536};
         plan.n_chunks = 7;
         memcpy(plan.cum, cum, sizeof(cum));
@@ -1300,9 +1357,11 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
     sc.hdr = share_setup ? (int *)(scratch + off_hdr) : nullptr;
     sc.rec = share_setup ? (uint32_t *)(scratch + off_rec) : nullptr;
     sc.no_pairs = getenv("BEVK_NO_PAIRS") ? 1 : 0;
-    sc.dbg = getenv("BEVK_DBG") ? atoi(getenv("BEVK_DBG")) : 0;
+    sc.dbg = (kExperiments && getenv("BEVK_DBG")) ? atoi(getenv("BEVK_DBG")) : 0;
     sc.slack = getenv("BEVK_SLACK") ? atoi(getenv("BEVK_SLACK")) : 0;
     sc.pf = getenv("BEVK_PF") ? atoi(getenv("BEVK_PF")) : -1;
+    sc.pf1 = getenv("BEVK_PF1") ? atoi(getenv("BEVK_PF1")) : kPrefetchAhead;
+    sc.row_major = getenv("BEVK_ROWMAJOR") ? atoi(getenv("BEVK_ROWMAJOR")) : 0;
     sc.max_fps = getenv("BEVK_MAXFPS") ? atoi(getenv("BEVK_MAXFPS")) : kMaxStageFrames;
     {
         // stride permutation of the tile rows: groups of y_group adjacent rows stay together (their

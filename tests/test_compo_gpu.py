@@ -144,3 +144,39 @@ def test_fused_bev_composite_full_size():
     b1 = compo.composite_bev_batch(B, F, M, Hb, Hf[0], (1024, 1024), fused=False)
     assert torch.equal(a1, b1)
     assert torch.equal(a1[0], a[0])
+
+
+@pytest.mark.parametrize("dsize", [(37, 22), (1023, 1023), (5, 3)])
+def test_single_frame_odd_bev_and_unaligned_views(dsize):
+    """One image into a BEV whose byte size is not a multiple of 4: the unfused route blends the
+    two halves of ONE concatenated warp output, so the mask half starts on an odd byte offset --
+    it must still work (the reference handles any size).  Same for user views at odd offsets."""
+    rng = np.random.default_rng(78)
+    B = rng.integers(0, 256, (1, 30, 41, 3), dtype=np.uint8)
+    F = rng.integers(0, 256, (1, 30, 41, 3), dtype=np.uint8)
+    M = rng.integers(0, 256, (1, 30, 41, 3), dtype=np.uint8)
+    H = _quad_h(rng, (41, 30), dsize, 0.2)
+    ref = _oracle_batch(B, F, M, H[None], H[None], dsize)
+    out = compo.composite_bev_batch(cu(B), cu(F), cu(M), H, H, dsize).cpu().numpy()
+    assert np.array_equal(out, ref)
+    # composite_reg_img on views that start 1, 2, 3 bytes into a buffer
+    flat = torch.from_numpy(rng.integers(0, 256, 3 * 30 * 41 * 3 + 16, dtype=np.uint8)).to(DEV)
+    for off in (1, 2, 3):
+        n = 30 * 41 * 3
+        bg, fg, mk = (flat[off + i * n: off + (i + 1) * n].view(30, 41, 3) for i in range(3))
+        ref = co.composite_reg_img(bg.cpu().numpy(), fg.cpu().numpy(), mk.cpu().numpy())
+        assert np.array_equal(compo.composite_reg_img(bg, fg, mk).cpu().numpy(), ref)
+
+
+def test_out_arguments_are_validated():
+    from bev_b200 import _native
+    a = torch.zeros((4, 8, 8, 3), dtype=torch.uint8, device=DEV)
+    with pytest.raises(ValueError):
+        _native.composite_u8c3(a, a, a, out=torch.zeros((3, 8, 8, 3), dtype=torch.uint8, device=DEV))
+    with pytest.raises(ValueError):
+        _native.composite_u8c3(a, a, a, out=torch.zeros((4, 8, 8, 3), dtype=torch.float32, device=DEV))
+    with pytest.raises(ValueError):
+        _native.composite_bev_u8c3(a[:1], a, a, np.eye(3), np.eye(3), (8, 8),
+                                   out=torch.zeros((2, 8, 8, 3), dtype=torch.uint8, device=DEV))
+    with pytest.raises(ValueError):  # resize: dst with too few frames would be written out of bounds
+        _native.resize(a, (4, 4), dst=torch.zeros((2, 4, 4, 3), dtype=torch.uint8, device=DEV))
