@@ -121,12 +121,12 @@ def reference_arm(args, wl):
     H = h_canon(hscale)
     if inverse:
         H = np.linalg.inv(H)
-    sample = min(n_frames, 32)
+    sample = n_frames  # the whole workload: every step is one pass of the reference loop over all frames
     np_dtype = "float32" if dtype == "float16" else dtype  # cv2 has no fp16 warp
     frames = [seeded_frame(1234 + i, ssize[1], ssize[0], ch, np_dtype) for i in range(sample)]
     run, kind, cores = ref_cpu.make_warp_runner()
-    for _ in range(max(args.warmup, 1)):
-        run(frames[:4], H, dsize, flags)
+    for _ in range(max(args.warmup, 1)):  # full passes: thread pool, page cache and clocks warm
+        run(frames, H, dsize, flags)
     times = []
     for _ in range(args.steps):
         t0 = time.perf_counter()
@@ -140,8 +140,9 @@ def reference_arm(args, wl):
         "scaling": "weak", "vs_baseline": None, "dtype": "u8" if dtype == "uint8" else dtype,
         "data": "synthetic",
         "config": {"workload": wl, "frames_per_step": sample, "src": list(ssize), "dst": list(dsize),
+                   "same_config": True,
                    "note": "each step = the reference loop (cv2.warpPerspective per frame, "
-                           "vis_homo.py:85-89) over a %d-frame sample of the workload" % sample},
+                           "vis_homo.py:85-89) over all %d frames of the workload" % sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": "%d steps x %d frames" % (args.steps, sample),
                          "cpu": ref_cpu.cpu_model()},
@@ -162,6 +163,13 @@ def ours(args, wl):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # The only collective is the send/recv gather of BEV batches into rank 0: give NCCL's
+        # point-to-point path all its channels (measured at N=2, tools/gather_probe.py: 543 GB/s
+        # into rank 0 with the default channel count, 598 GB/s with 64, and no longer sensitive
+        # to the slice size the pipelined gather uses).
+        for k, v in (("NCCL_MIN_P2P_NCHANNELS", "64"), ("NCCL_MAX_P2P_NCHANNELS", "64"),
+                     ("NCCL_MAX_NCHANNELS", "64")):
+            os.environ.setdefault(k, v)
         dist.init_process_group("nccl", device_id=dev)
 
     n_frames, ssize, dsize, ch, dtype, flags, hscale, inverse = WORKLOADS[wl]
@@ -242,24 +250,96 @@ def ours(args, wl):
     up0, up1 = _native.warp_host_rows(ssize, dsize, H, flags)  # only referenced rows are uploaded
     h2d = n_frames * (up1 - up0 + 1) * row_bytes
     d2h = out.numel() * es
+    # What the host link allows for these byte counts: plain pinned copies of h2d bytes up and
+    # d2h bytes down at the same time, on every rank at once (the ranks share the host's memory
+    # and PCIe root complexes) -- the ceiling of the e2e number at this N.
+    pcie = None
+    if not args.no_e2e:
+        d_up = torch.empty(h2d, dtype=torch.uint8, device=dev)
+        h_up = h_src.view(torch.uint8).reshape(-1)[:h2d]
+        h_dn = h_dst.view(torch.uint8).reshape(-1)
+        d_dn = out.view(torch.uint8).reshape(-1)
+        s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        best = None
+        for _ in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            with torch.cuda.stream(s_up):
+                d_up.copy_(h_up, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                h_dn.copy_(d_dn, non_blocking=True)
+            s_up.synchronize()
+            s_dn.synchronize()
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            best = float(tt.item()) if best is None else min(best, float(tt.item()))
+        pcie = {"copy_ms": best * 1e3, "GBps_per_gpu_both_directions": (h2d + d2h) / best / 1e9,
+                "GBps_box_total": world * (h2d + d2h) / best / 1e9,
+                "ceiling_Mpix_s": world * px_step / best / 1e6,
+                "e2e_frac_of_ceiling": e2e_value / (world * px_step / best / 1e6)}
+        del d_up, h_src, h_dst
 
-    # ---- gather of BEV outputs to rank 0 (reported separately from the warp scaling)
+    # ---- gather of BEV outputs to rank 0 (reported separately from the warp scaling):
+    #      once after the warp, and once chunk-pipelined behind the warp on a side stream
     gather = None
     if world > 1:
+        out_bytes = out.numel() * es
         sharding.gather_to_rank0(out[:2])  # connection set-up is not part of the measurement
         torch.cuda.synchronize()
         dist.barrier()
+
+        def max_ms(ms):
+            tg = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+            return float(tg.item())
+
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        gathered = sharding.gather_to_rank0(out)
-        g1.record()
-        torch.cuda.synchronize()
-        tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
-        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-        gms = float(tg.item())
-        gather = {"ms": gms, "bytes_into_rank0": (world - 1) * out.numel() * es,
-                  "GBps_into_rank0": (world - 1) * out.numel() * es / (gms * 1e-3) / 1e9}
-        del gathered
+        gms = None
+        for _ in range(3):  # the first pass also pays for the 1.6 GB receive buffer's allocation
+            barrier()
+            g0.record()
+            gathered = sharding.gather_to_rank0(out, chunks=1)
+            g1.record()
+            torch.cuda.synchronize()
+            ms_g = max_ms(g0.elapsed_time(g1))
+            gms = ms_g if gms is None else min(gms, ms_g)
+            del gathered
+
+        def produce(b, e, dst):
+            homo.warp_perspective(frames[b:e], H, dsize, dst=dst[b:e], flags=flags)
+
+        best = None
+        for _ in range(3):
+            barrier()
+            g0.record()
+            _, gathered = sharding.pipelined_gather_to_rank0(
+                produce, n_frames, tuple(out.shape[1:]), tdtype, dev, chunks=8, local_out=out)
+            g1.record()
+            torch.cuda.synchronize()
+            pms = max_ms(g0.elapsed_time(g1))
+            best = pms if best is None else min(best, pms)
+            del gathered
+        into0 = (world - 1) * out_bytes
+        gather = {"ms": gms, "bytes_into_rank0": into0, "GBps_into_rank0": into0 / (gms * 1e-3) / 1e9,
+                  "pipelined": {"ms_warp_and_gather": best, "chunks": 8,
+                                "GBps_into_rank0": into0 / (best * 1e-3) / 1e9,
+                                "Mpix_s_gathered_on_rank0": world * px_step / (best * 1e-3) / 1e6,
+                                "note": "8 frame slices: warp of slice k+1 on the compute stream while "
+                                        "slice k is gathered (NCCL send/recv) on a side stream"},
+                  "ingress_peak_GBps": {"nominal": 900.0, "measured_peer_copy": 770.0},
+                  "limiting": "rank 0's NVLink ingress: (N-1) x %.0f MB must enter one GPU, the warp "
+                              "that produces them takes %.2f ms per rank" % (out_bytes / 1e6, ms_per_step)}
+
+    # ---- the other sharded workloads of BASELINE.json at N > 1
+    multi = None
+    if world > 1 and not args.no_other_configs:
+        del frames, out
+        torch.cuda.empty_cache()
+        multi = {"projection": projection_leg(dev, min(args.steps, 20), 0.0, False, world=world),
+                 "cfg4_sharded": cfg4_sharded(dev, rank, world, min(args.steps, 5))}
+        frames = out = None
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -282,12 +362,12 @@ def ours(args, wl):
                        "interp": "bilinear" if flags & 1 else "nearest",
                        "homography": "H_canon (SURVEY 8d)", "parallelism": "frames sharded, %d per GPU" % n_frames,
                        "l2": "inputs %.0f MB per step >> 126 MB L2, no flush needed"
-                             % (frames.numel() * es / 1e6),
+                             % (n_frames * ssize[0] * ssize[1] * ch * es / 1e6),
                        "kernel_path": args.path or "auto"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "api": "bevk_warp_perspective_host (pinned host src/dst)"},
+                    "api": "bevk_warp_perspective_host (pinned host src/dst)", "pcie": pcie},
             "gpu_launches": args.steps * 1,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -298,9 +378,11 @@ def ours(args, wl):
         }
         if gather:
             line["gather"] = gather
+        if multi:
+            line.update(multi)
         if world == 1 and not args.no_cpu_baseline:
             from oracle import ref_cpu
-            sample = min(n_frames, 32)
+            sample = n_frames  # the same 256 frames the GPU arm warps (and --impl reference times)
             host = frames[:sample].cpu()
             if tdtype == torch.float16:
                 host = host.to(torch.float32)
@@ -322,16 +404,19 @@ def ours(args, wl):
         dist.destroy_process_group()
 
 
-def projection_leg(dev, steps, cpu_seconds, with_cpu):
+def projection_leg(dev, steps, cpu_seconds, with_cpu, world=1):
     """BASELINE configs[2]: 10 M synthetic xywh-theta BEV boxes -> image corners and back (fp32),
     through bev_b200.rbox_torch (one fused CUDA kernel per direction).  Returns the `projection`
     object of the JSON line: projections/s (one box through one direction), the HBM roofline of
     the two kernels (52 B per box and direction) and the reference's numpy float64
-    chain timed on a bounded sample of the same boxes."""
+    chain timed on a bounded sample of the same boxes.  world > 1: every rank projects its own
+    10 M boxes (weak scaling, no exchange), time = max over ranks, value = all ranks' boxes."""
     import torch
+    import torch.distributed as dist
     from bev_b200 import rbox_torch
     n = 10_000_000
-    g = torch.Generator(device=dev).manual_seed(0)
+    seed = 0 + (dist.get_rank() if world > 1 else 0)
+    g = torch.Generator(device=dev).manual_seed(seed)
     u = torch.rand((n, 5), dtype=torch.float32, device=dev, generator=g)
     lo = torch.tensor([0.0, 0.0, 4.0, 8.0, -np.pi], dtype=torch.float32, device=dev)
     hi = torch.tensor([1024.0, 1024.0, 40.0, 120.0, np.pi], dtype=torch.float32, device=dev)
@@ -343,6 +428,8 @@ def projection_leg(dev, steps, cpu_seconds, with_cpu):
         img = rbox_torch.xywhr_to_img_corners(box, H_fwd, "bev")
         back = rbox_torch.img_corners_to_xywhr(img, H_back, "bev")
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
@@ -351,14 +438,18 @@ def projection_leg(dev, steps, cpu_seconds, with_cpu):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
     peak, peak_src = measured_peak()
     algo = 2 * 52 * n
-    out = {"metric": "rbox projections/s", "value": 2 * n / (ms * 1e-3) / 1e6, "unit": "Mproj/s",
-           "boxes": n, "ms_fwd_plus_back": ms, "dtype": "f32 io, f64 registers",
-           "gpu_launches_per_step": 2,
+    out = {"metric": "rbox projections/s", "value": world * 2 * n / (ms * 1e-3) / 1e6, "unit": "Mproj/s",
+           "boxes_per_gpu": n, "n_gpus": world, "ms_fwd_plus_back": ms, "dtype": "f32 io, f64 registers",
+           "gpu_launches_per_step": "2 bulk kernels (+ 2 one-block tail launches when n % 256 != 0)",
            "roofline": {"bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "peak": peak,
                         "unit": "GB/s", "frac": algo / (ms * 1e-3) / 1e9 / peak,
-                        "algo_bytes_per_step": algo, "peak_source": peak_src},
+                        "algo_bytes_per_step": algo, "peak_source": peak_src, "per": "GPU"},
            "round_trip_max_abs_err": float((back[:, :4] - box[:, :4]).abs().max().item())}
     if with_cpu:
         from oracle import ref_cpu
@@ -366,6 +457,59 @@ def projection_leg(dev, steps, cpu_seconds, with_cpu):
         cb = ref_cpu.time_rbox_chain(sample, H_fwd, H_back, "bev", min_seconds=cpu_seconds)
         out["cpu_baseline"] = cb
     return out
+
+
+def cfg4_sharded(dev, rank, world, steps, n_frames=1000):
+    """BASELINE configs[3] on N GPUs: the eight BrnoCompSpeed-shaped camera streams of
+    tests/golden/cfg4_cams.json, 1000 synthetic 1080p frames each, dealt to the ranks by
+    sharding.shard_cameras (N = 8: one stream per GPU, 4: two, 2: four).  Every rank warps its
+    own streams, nothing is exchanged; time = max over ranks of the rank's total."""
+    import torch
+    import torch.distributed as dist
+    from bev_b200 import _native, homo, sharding
+    cams = json.load(open(os.path.join(ROOT, "tests", "golden", "cfg4_cams.json")))
+    mine = sharding.shard_cameras(len(cams), rank, world)
+    peak, _ = measured_peak()
+    per_cam, my_ms, my_px, my_bytes = {}, 0.0, 0, 0
+    for k in mine:
+        c = cams[k]
+        H = np.array(c["H_bev_img"])
+        dsize = (int(c["bspec"]["u_size"]), int(c["bspec"]["v_size"]))
+        g = torch.Generator(device=dev).manual_seed(1234 + k)
+        frames = torch.randint(0, 256, (n_frames, 1080, 1920, 3), dtype=torch.uint8, device=dev, generator=g)
+        dst = torch.empty((n_frames, dsize[1], dsize[0], 3), dtype=torch.uint8, device=dev)
+        T, _, _ = _native.warp_touched_pixels((1920, 1080), dsize, H, 1)
+        for _ in range(2):
+            homo.warp_perspective(frames, H, dsize, dst=dst)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            homo.warp_perspective(frames, H, dsize, dst=dst)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        per_cam[str(c.get("id", k))] = {"bev": list(dsize), "ms": ms}
+        my_ms += ms
+        my_px += n_frames * dsize[0] * dsize[1]
+        my_bytes += (T + dsize[0] * dsize[1]) * 3 * n_frames
+        del frames, dst
+        torch.cuda.empty_cache()
+    t = torch.tensor([my_ms, float(my_px), float(my_bytes)], dtype=torch.float64, device=dev)
+    tmax, tsum = t.clone(), t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    ms_max, ms_sum = float(tmax[0].item()), float(tsum[0].item())
+    px, nbytes = float(tsum[1].item()), float(tsum[2].item())
+    return {"cameras": len(cams), "frames_per_camera": n_frames, "cameras_of_rank0": mine,
+            "ms": ms_max, "Mpix_s": px / ms_max / 1e3,
+            "roofline_frac_per_gpu": nbytes / world / (ms_max * 1e-3) / 1e9 / peak,
+            "n1_equivalent_ms": ms_sum,
+            "efficiency": ms_sum / (world * ms_max),
+            "rank0_per_camera": per_cam,
+            "note": "ms = slowest rank's total over its cameras (one launch per camera); "
+                    "n1_equivalent_ms = sum over all cameras of the single-GPU kernel time; "
+                    "efficiency = that / (N x ms): below 1 only through the uneven BEV sizes of the streams"}
 
 
 def other_configs(dev, steps):
