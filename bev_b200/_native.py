@@ -33,6 +33,8 @@ SIGNATURES = {
     "bevk_invert3x3": (_c_int, [_dp, _dp]),
     "bevk_warp_perspective": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                        _c_int, _dp, _c_int, _i32p, _c_int, _c_int, _dp, _vp]),
+    "bevk_warp_perspective_path": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                            _c_int, _dp, _c_int, _i32p, _c_int, _c_int, _dp, _c_int, _vp]),
     "bevk_warp_perspective_host": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int,
                                             _c_int, _c_int, _dp, _c_int, _i32p, _c_int, _c_int,
                                             _dp]),
@@ -200,8 +202,13 @@ def _frames_view(src):
     raise ValueError("src must be (H,W), (H,W,C) or (N,H,W,C); got shape %s" % (tuple(src.shape),))
 
 
+_PATHS = {None: -1, "auto": 0, "generic": 1, "fast": 2}
+
+
 def warp_perspective(src, M, dsize, dst=None, flags=1, borderMode=0, borderValue=0,
-                     mat_index=None):
+                     mat_index=None, path=None):
+    """path: None (the calling thread's default, see set_warp_path), "auto", "generic" (direct-gather
+    kernels) or "fast" (staged kernel; raises if the shape does not qualify)."""
     import torch
     _require_cuda(src, "src")
     code = _warp_dtype(src)
@@ -222,10 +229,10 @@ def warp_perspective(src, M, dsize, dst=None, flags=1, borderMode=0, borderValue
         out4 = torch.empty((n, dh, dw, c), dtype=src.dtype, device=src.device)
     b = _border(borderValue)
     with torch.cuda.device(src.device):
-        rc = lib().bevk_warp_perspective(
+        rc = lib().bevk_warp_perspective_path(
             _vp(s4.data_ptr()), _vp(out4.data_ptr()), n, h, w, dh, dw, c, code, _dptr(Ms),
             Ms.shape[0], idx.ctypes.data_as(_i32p) if idx is not None else None, int(flags),
-            int(borderMode), _dptr(b), _stream_ptr(src))
+            int(borderMode), _dptr(b), _PATHS.get(path, path), _stream_ptr(src))
     _check(rc, "bevk_warp_perspective")
     return dst if dst is not None else undo(out4)
 

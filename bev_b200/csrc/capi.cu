@@ -54,7 +54,7 @@ int bevk_require_device(void)
 
 int bevk_sm_count(void) { return g_sm_count > 0 ? g_sm_count : 148; }
 
-static int g_warp_path = 0;
+static thread_local int g_warp_path = 0;  // default kernel family of the calling thread (testing aid)
 
 extern "C" {
 
@@ -209,7 +209,7 @@ void build_groups(int n_frames, int n_mats, const int32_t *mat_index, const std:
 }
 
 int run_warp_device(const void *src, void *dst, const WarpArgs &a,
-                    const std::vector<BevkWarpGroup> &groups, cudaStream_t stream)
+                    const std::vector<BevkWarpGroup> &groups, int path, cudaStream_t stream)
 {
     BevkWarpParams p;
     memset(&p, 0, sizeof(p));
@@ -229,10 +229,10 @@ int run_warp_device(const void *src, void *dst, const WarpArgs &a,
         p.n_groups = ng;
         for (int i = 0; i < ng; ++i) p.g[i] = groups[g0 + i];
         int launched = 0;
-        if (g_warp_path != 1) {
-            launched = bevk_launch_warp_fast(p, a.channels, a.dtype, a.linear, g_warp_path == 2, stream);
+        if (path != 1) {
+            launched = bevk_launch_warp_fast(p, a.channels, a.dtype, a.linear, path == 2, stream);
             if (launched < 0) return launched;
-            if (!launched && g_warp_path == 2)
+            if (!launched && path == 2)
                 BEVK_FAIL(BEVK_E_ARG, "warp: shape does not qualify for the staged fast path");
         }
         if (!launched) {
@@ -325,6 +325,17 @@ int bevk_warp_perspective(const void *src, void *dst, int n_frames, int src_h, i
                           int n_mats, const int32_t *mat_index, int flags, int border_mode,
                           const double *border_value, void *stream)
 {
+    return bevk_warp_perspective_path(src, dst, n_frames, src_h, src_w, dst_h, dst_w, channels, dtype, M,
+                                      n_mats, mat_index, flags, border_mode, border_value, -1, stream);
+}
+
+int bevk_warp_perspective_path(const void *src, void *dst, int n_frames, int src_h, int src_w,
+                               int dst_h, int dst_w, int channels, int dtype, const double *M,
+                               int n_mats, const int32_t *mat_index, int flags, int border_mode,
+                               const double *border_value, int path, void *stream)
+{
+    if (path < -1 || path > 2) BEVK_FAIL(BEVK_E_ARG, "warp: path must be -1 (thread default), 0, 1 or 2");
+    if (path < 0) path = g_warp_path;
     WarpArgs a;
     int rc = check_warp_args(src, dst, n_frames, src_h, src_w, dst_h, dst_w, channels, dtype, M,
                              n_mats, mat_index, flags, border_mode, border_value, a);
@@ -336,7 +347,7 @@ int bevk_warp_perspective(const void *src, void *dst, int n_frames, int src_h, i
     effective_maps(M, n_mats, flags, maps);
     std::vector<BevkWarpGroup> groups;
     build_groups(n_frames, n_mats, mat_index, maps, groups);
-    return run_warp_device(src, dst, a, groups, (cudaStream_t)stream);
+    return run_warp_device(src, dst, a, groups, path, (cudaStream_t)stream);
 }
 
 int bevk_warp_host_rows(int src_h, int src_w, int dst_h, int dst_w, const double *M, int n_mats,
@@ -440,7 +451,7 @@ int bevk_warp_perspective_host(const void *src, void *dst, int n_frames, int src
         build_groups(nf, use_n_mats, idx_ptr, *use_maps, groups);
         WarpArgs ac = a;
         ac.n_frames = nf;
-        rc = run_warp_device(g_ws.d_src[slot], g_ws.d_dst[slot], ac, groups, st);
+        rc = run_warp_device(g_ws.d_src[slot], g_ws.d_dst[slot], ac, groups, g_warp_path, st);
         if (rc) {
             cudaDeviceSynchronize();
             return rc;

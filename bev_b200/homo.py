@@ -206,7 +206,7 @@ def compose_H_bev_img(calib, bspec):
 
 
 def warp_perspective(src, M, dsize, dst=None, flags=INTER_LINEAR, borderMode=BORDER_CONSTANT,
-                     borderValue=0, mat_index=None):
+                     borderValue=0, mat_index=None, path=None):
     """Drop-in for ``cv2.warpPerspective(src, M, dsize[, dst, flags, borderMode, borderValue])``
     on CUDA tensors, batched.
 
@@ -221,9 +221,10 @@ def warp_perspective(src, M, dsize, dst=None, flags=INTER_LINEAR, borderMode=BOR
 
     uint8/float32 results are bit-identical to cv2 4.13 (nearest and bilinear); float16 equals
     float16(cv2(float32(src))).  Only BORDER_CONSTANT is implemented (all reference call sites
-    use the default).
+    use the default).  ``path`` ("auto" / "generic" / "fast") pins the kernel family for this call
+    (tests and benchmarks); None leaves the choice to the library.
     """
-    return _native.warp_perspective(src, M, dsize, dst, flags, borderMode, borderValue, mat_index)
+    return _native.warp_perspective(src, M, dsize, dst, flags, borderMode, borderValue, mat_index, path)
 
 
 def warp_img_to_bev(frames, calib, bspec, flags=INTER_LINEAR):

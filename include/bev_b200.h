@@ -89,9 +89,19 @@ int bevk_warp_perspective_host(const void *src, void *dst, int n_frames, int src
 int bevk_warp_host_rows(int src_h, int src_w, int dst_h, int dst_w, const double *M, int n_mats,
                         int flags, int rows[2]);
 
-/* Selects the kernel family for bevk_warp_perspective: 0 = automatic (default), 1 = force the
- * generic gather kernel, 2 = force the staged fast path (errors if the shape does not qualify).
- * Testing / benchmarking aid; process-wide. */
+/* bevk_warp_perspective with the kernel family chosen per call: path 0 = automatic, 1 = the
+ * direct-gather kernels, 2 = the staged (TMA) kernel (BEVK_E_ARG if the shape does not qualify),
+ * -1 = the calling thread's default (bevk_warp_set_path).  Same reference interface as
+ * bevk_warp_perspective (vis_homo.py:85-91); the extra argument exists for tests and benchmarks
+ * that compare the kernel families. */
+int bevk_warp_perspective_path(const void *src, void *dst, int n_frames, int src_h, int src_w,
+                               int dst_h, int dst_w, int channels, int dtype, const double *M,
+                               int n_mats, const int32_t *mat_index, int flags, int border_mode,
+                               const double *border_value, int path, void *stream);
+
+/* Default kernel family of the CALLING THREAD for bevk_warp_perspective / _host (0 automatic --
+ * the initial value --, 1 direct-gather, 2 staged).  Thread-local: it never affects other
+ * threads' calls.  Testing / benchmarking aid. */
 int bevk_warp_set_path(int path);
 
 /*

@@ -272,6 +272,13 @@ def gen_warp():
     small["n"] = np.array(idx)
     np.savez_compressed(os.path.join(OUT, "warp_small.npz"), **small)
 
+    gen_warp_hashes()
+
+
+def gen_warp_hashes():
+    """sha256 of cv2's full-size outputs on seeded frames (tests/golden/warp_hash.json).  float16
+    cases: cv2 has no float16 warp, the contract is float16(cv2(float32(src))), so
+    the seeded float16 frame is upcast, warped by cv2 in float32 and rounded once to float16."""
     hashes = []
     Hc, Hc4 = h_canon(), h_canon(2)
     full = [
@@ -287,6 +294,14 @@ def gen_warp():
         ("cfg5_4k_to_2048_lin_f32", 1238, (2160, 3840, 3), "float32", Hc4, (2048, 2048), 1),
         ("c1_1080p_to_1024_lin", 1239, (1080, 1920, 1), "uint8", Hc, (1024, 1024), 1),
         ("c4_1080p_to_1024_lin", 1240, (1080, 1920, 4), "uint8", Hc, (1024, 1024), 1),
+        # BASELINE configs[4] in both directions and both dtypes, bilinear and nearest
+        ("cfg5_inv_2048_to_4k_nn", 1237, (2048, 2048, 3), "uint8", np.linalg.inv(Hc4), (3840, 2160), 0),
+        ("cfg5_4k_to_2048_lin_f16", 1241, (2160, 3840, 3), "float16", Hc4, (2048, 2048), 1),
+        ("cfg5_4k_to_2048_nn_f16", 1241, (2160, 3840, 3), "float16", Hc4, (2048, 2048), 0),
+        ("cfg5_inv_2048_to_4k_lin_f16", 1242, (2048, 2048, 3), "float16", np.linalg.inv(Hc4),
+         (3840, 2160), 1),
+        ("cfg5_inv_2048_to_4k_nn_f16", 1242, (2048, 2048, 3), "float16", np.linalg.inv(Hc4),
+         (3840, 2160), 0),
     ]
     for k in range(8):
         _, bspec, H, sid = cfg4_camera(k)
@@ -296,7 +311,10 @@ def gen_warp():
         img = seeded_frame(seed, *shape, dtype)
         if shape[2] == 1:
             img = img[:, :, 0]
-        out = cv2.warpPerspective(img, H, dsize, flags=flags)
+        if dtype == "float16":
+            out = cv2.warpPerspective(img.astype(np.float32), H, dsize, flags=flags).astype(np.float16)
+        else:
+            out = cv2.warpPerspective(img, H, dsize, flags=flags)
         hashes.append({"name": name, "seed": seed, "shape": list(shape), "dtype": dtype,
                        "H": L(H), "dsize": list(dsize), "flags": flags,
                        "sha256": hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest(),
@@ -446,6 +464,9 @@ def gen_iou():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "warp_hash":
+        gen_warp_hashes()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "compo":
         gen_compo()
         sys.exit(0)

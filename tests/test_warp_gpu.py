@@ -347,3 +347,96 @@ def test_fuzz_paths_agree_on_random_homographies():
                 assert util.bits_equal(outs["generic"][n - 1], ref), (case, "oracle")
     finally:
         _native.set_warp_path("auto")
+
+
+@pytest.mark.parametrize("dtype", ["uint8", "float16"])
+@pytest.mark.parametrize("inverse", [False, True])
+@pytest.mark.parametrize("flags", [1, 0])
+def test_cfg5_full_batch(flags, inverse, dtype):
+    """BASELINE configs[4] at full size: 64 frames, 4K -> 2048^2 and 2048^2 -> 4K, uint8 and float16,
+    bilinear and nearest, one call each.  The batch holds every frame twice (i and i + 32): both
+    halves of the output must agree whatever chunk, tile, ring slot or kernel path a frame took;
+    three frames are compared bit for bit with the oracle (float16: float16(oracle(float32)))."""
+    H = util.h_canon(2)
+    ssize, dsize = (3840, 2160), (2048, 2048)
+    if inverse:
+        H, ssize, dsize = np.linalg.inv(H), dsize, ssize
+    g = torch.Generator(device=DEV).manual_seed(11 + flags)
+    half = torch.randint(0, 256, (32, ssize[1], ssize[0], 3), dtype=torch.uint8, device=DEV, generator=g)
+    if dtype == "float16":
+        half = (half.to(torch.float32) / 255.0).to(torch.float16)
+    frames = torch.cat([half, half], 0)
+    del half
+    out = homo.warp_perspective(frames, H, dsize, flags=flags)
+    assert tuple(out.shape) == (64, dsize[1], dsize[0], 3) and out.dtype == frames.dtype
+    assert torch.equal(out[:32].view(torch.uint8), out[32:].view(torch.uint8))
+    for i in (0, 21, 63):
+        ref = wo.warp_perspective(frames[i].cpu().numpy(), H, dsize, flags)
+        assert util.bits_equal(out[i].cpu().numpy(), ref), (flags, inverse, dtype, i)
+
+
+def test_cfg4_shaped_call_eight_matrices_one_launch(path):
+    """BASELINE configs[3] in one call: 1080p frames of eight camera streams interleaved in one
+    batch, a table of eight homographies and a per-frame camera index (one launch serves several
+    cameras).  The eight cameras of tests/golden/cfg4_cams.json stretched to one
+    common 1024 x 1024 BEV so that they fit a single output tensor; every frame against the oracle."""
+    import json
+    import os
+    cams = json.load(open(os.path.join(util.GOLDEN, "cfg4_cams.json")))
+    Hs = []
+    for c in cams:
+        w, h = int(c["bspec"]["u_size"]), int(c["bspec"]["v_size"])
+        S = np.diag([1024.0 / w, 1024.0 / h, 1.0])
+        Hs.append(S @ np.array(c["H_bev_img"], np.float64))
+    Hs = np.stack(Hs)
+    n = 24
+    idx = np.array([(5 * i) % 8 for i in range(n)], np.int32)  # cameras interleaved, 3 frames each
+    frames = np.stack([util.seeded_frame(4000 + i, 1080, 1920, 3, "uint8") for i in range(n)])
+    out = gpu_warp(frames, Hs, (1024, 1024), 1, mat_index=idx)
+    for i in range(n):
+        ref = wo.warp_perspective(frames[i], Hs[idx[i]], (1024, 1024), flags=1)
+        assert util.bits_equal(out[i], ref), (path, i, int(idx[i]))
+
+
+def test_concurrent_streams_and_threads():
+    """Launches from several CUDA streams and two host threads at once: every launch owns its
+    stream-ordered scratch (item counter, split flags, set-up records), so results must stay
+    bit-identical to a serial run.  Camera homographies at 1024^2 give split launches (staged +
+    direct-gather kernel), H_canon a plain staged one."""
+    import json
+    import os
+    import threading
+    cams = json.load(open(os.path.join(util.GOLDEN, "cfg4_cams.json")))
+    c = cams[2]
+    w, h = int(c["bspec"]["u_size"]), int(c["bspec"]["v_size"])
+    H_cam = np.diag([1024.0 / w, 1024.0 / h, 1.0]) @ np.array(c["H_bev_img"], np.float64)
+    jobs = [(util.h_canon(), 1, "auto"), (H_cam, 1, "auto"), (util.h_canon(), 0, "fast"), (H_cam, 1, "generic")]
+    g = torch.Generator(device=DEV).manual_seed(3)
+    frames = torch.randint(0, 256, (12, 1080, 1920, 3), dtype=torch.uint8, device=DEV, generator=g)
+    serial = [homo.warp_perspective(frames, H, (1024, 1024), flags=f) for H, f, _ in jobs]
+    torch.cuda.synchronize()
+    results, errors = {}, []
+
+    def worker(tid):
+        try:
+            streams = [torch.cuda.Stream(device=DEV) for _ in range(4)]
+            outs = []
+            for rep in range(6):
+                for j, (H, f, pth) in enumerate(jobs):  # the kernel family is a per-call argument
+                    with torch.cuda.stream(streams[(j + rep) % 4]):
+                        outs.append((j, homo.warp_perspective(frames, H, (1024, 1024), flags=f, path=pth)))
+            for st in streams:
+                st.synchronize()
+            results[tid] = outs
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for tid in results:
+        for j, o in results[tid]:
+            assert torch.equal(o, serial[j]), (tid, j)
