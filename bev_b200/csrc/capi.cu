@@ -20,39 +20,70 @@ void bevk_set_error(const char *fmt, ...)
     va_end(ap);
 }
 
-static int g_dev_state = 0;  // 0 unknown, 1 ok, -1 unusable
-static int g_sm_count = 0, g_cc_major = 0, g_cc_minor = 0;
+// Per-device probe results (a process may drive several B200s: one state per device ordinal).
+constexpr int kMaxDevices = 64;
+struct DeviceProbe {
+    int state = 0;  // 0 unknown, 1 ok, -1 unusable
+    int sm_count = 0, cc_major = 0, cc_minor = 0;
+};
+static DeviceProbe g_probe[kMaxDevices];
+static int g_no_device = 0;  // 1: the runtime reports no CUDA device at all
 static std::mutex g_dev_mutex;
+
+static DeviceProbe *current_probe()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return &g_probe[dev];
+}
 
 int bevk_require_device(void)
 {
     std::lock_guard<std::mutex> lock(g_dev_mutex);
-    if (g_dev_state == 0) {
-        int dev = 0, n = 0;
+    DeviceProbe *pr = nullptr;
+    if (!g_no_device) {
+        int n = 0;
         cudaError_t e = cudaGetDeviceCount(&n);
         if (e != cudaSuccess || n == 0) {
-            g_dev_state = -1;
+            g_no_device = 1;
             cudaGetLastError();
         } else {
-            cudaGetDevice(&dev);
-            cudaDeviceProp prop;
-            cudaGetDeviceProperties(&prop, dev);
-            g_sm_count = prop.multiProcessorCount;
-            g_cc_major = prop.major;
-            g_cc_minor = prop.minor;
-            g_dev_state = (prop.major == 10) ? 1 : -1;
+            pr = current_probe();
         }
     }
-    if (g_dev_state < 0) {
+    if (pr && pr->state == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) {
+            pr->sm_count = prop.multiProcessorCount;
+            pr->cc_major = prop.major;
+            pr->cc_minor = prop.minor;
+            pr->state = (prop.major == 10) ? 1 : -1;
+        } else {
+            cudaGetLastError();
+            pr->state = -1;
+        }
+    }
+    if (!pr || pr->state < 0) {
         bevk_set_error("libbev_b200 needs an sm_100 (B200) CUDA device; found %s (cc %d.%d). "
                        "There is no CPU fallback.",
-                       g_sm_count ? "an unsupported GPU" : "no usable GPU", g_cc_major, g_cc_minor);
+                       pr && pr->sm_count ? "an unsupported GPU" : "no usable GPU", pr ? pr->cc_major : 0,
+                       pr ? pr->cc_minor : 0);
         return BEVK_E_NOGPU;
     }
     return BEVK_OK;
 }
 
-int bevk_sm_count(void) { return g_sm_count > 0 ? g_sm_count : 148; }
+int bevk_sm_count(void)
+{
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    DeviceProbe *pr = current_probe();
+    return (pr && pr->sm_count > 0) ? pr->sm_count : 148;
+}
 
 static thread_local int g_warp_path = 0;  // default kernel family of the calling thread (testing aid)
 
@@ -64,9 +95,11 @@ const char *bevk_last_error(void) { return g_err; }
 int bevk_device_info(int *sm_count, int *cc_major, int *cc_minor)
 {
     int rc = bevk_require_device();
-    if (sm_count) *sm_count = g_sm_count;
-    if (cc_major) *cc_major = g_cc_major;
-    if (cc_minor) *cc_minor = g_cc_minor;
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    DeviceProbe *pr = current_probe();
+    if (sm_count) *sm_count = pr ? pr->sm_count : 0;
+    if (cc_major) *cc_major = pr ? pr->cc_major : 0;
+    if (cc_minor) *cc_minor = pr ? pr->cc_minor : 0;
     return rc;
 }
 
@@ -303,8 +336,9 @@ void referenced_rows_union(const std::vector<double> &maps, int n_mats, const Wa
     }
 }
 
-// grow-only device workspace for the host-buffer entry point: kHostSlots chunks in flight, each
-// with its own stream and device buffers
+// grow-only device workspace of the host-buffer entry point, one per device: kHostSlots chunks in
+// flight, each with its own stream and device buffers.  A workspace is only ever touched under its
+// own mutex and is never freed because another device is being used.
 constexpr int kHostSlots = 3;
 struct HostWorkspace {
     std::mutex mu;
@@ -312,9 +346,9 @@ struct HostWorkspace {
     void *d_dst[kHostSlots] = {};
     size_t src_cap = 0, dst_cap = 0;
     cudaStream_t stream[kHostSlots] = {};
-    int device = -1;
+    bool ready = false;
 };
-HostWorkspace g_ws;
+HostWorkspace g_ws[kMaxDevices];
 
 }  // namespace
 
@@ -395,43 +429,57 @@ int bevk_warp_perspective_host(const void *src, void *dst, int n_frames, int src
     chunk = std::min(chunk, std::max(1, (n_frames + 3) / 4));
     chunk = std::min(chunk, n_frames);
 
-    std::lock_guard<std::mutex> lock(g_ws.mu);
     int dev = 0;
     BEVK_CUDA(cudaGetDevice(&dev));
-    if (g_ws.device != dev) {
-        for (int i = 0; i < kHostSlots; ++i) {
-            if (g_ws.d_src[i]) cudaFree(g_ws.d_src[i]);
-            if (g_ws.d_dst[i]) cudaFree(g_ws.d_dst[i]);
-            g_ws.d_src[i] = g_ws.d_dst[i] = nullptr;
-            if (g_ws.stream[i]) cudaStreamDestroy(g_ws.stream[i]);
-            BEVK_CUDA(cudaStreamCreateWithFlags(&g_ws.stream[i], cudaStreamNonBlocking));
-        }
-        g_ws.src_cap = g_ws.dst_cap = 0;
-        g_ws.device = dev;
+    if (dev < 0 || dev >= kMaxDevices) BEVK_FAIL(BEVK_E_ARG, "warp: device ordinal %d is not supported", dev);
+    HostWorkspace &ws = g_ws[dev];
+    std::lock_guard<std::mutex> lock(ws.mu);  // concurrent host calls on one device take turns
+    if (!ws.ready) {
+        for (int i = 0; i < kHostSlots; ++i)
+            BEVK_CUDA(cudaStreamCreateWithFlags(&ws.stream[i], cudaStreamNonBlocking));
+        ws.ready = true;
     }
-    if (g_ws.src_cap < src_frame_bytes * chunk) {
+    if (ws.src_cap < src_frame_bytes * chunk) {
         for (int i = 0; i < kHostSlots; ++i) {
-            if (g_ws.d_src[i]) cudaFree(g_ws.d_src[i]);
-            g_ws.d_src[i] = nullptr;
-            BEVK_CUDA(cudaMalloc(&g_ws.d_src[i], src_frame_bytes * chunk));
+            // the previous call synchronised every slot stream before it returned: nothing is in flight
+            if (ws.d_src[i]) cudaFree(ws.d_src[i]);
+            ws.d_src[i] = nullptr;
         }
-        g_ws.src_cap = src_frame_bytes * chunk;
+        ws.src_cap = 0;
+        for (int i = 0; i < kHostSlots; ++i) BEVK_CUDA(cudaMalloc(&ws.d_src[i], src_frame_bytes * chunk));
+        ws.src_cap = src_frame_bytes * chunk;
     }
-    if (g_ws.dst_cap < dst_frame_bytes * chunk) {
+    if (ws.dst_cap < dst_frame_bytes * chunk) {
         for (int i = 0; i < kHostSlots; ++i) {
-            if (g_ws.d_dst[i]) cudaFree(g_ws.d_dst[i]);
-            g_ws.d_dst[i] = nullptr;
-            BEVK_CUDA(cudaMalloc(&g_ws.d_dst[i], dst_frame_bytes * chunk));
+            if (ws.d_dst[i]) cudaFree(ws.d_dst[i]);
+            ws.d_dst[i] = nullptr;
         }
-        g_ws.dst_cap = dst_frame_bytes * chunk;
+        ws.dst_cap = 0;
+        for (int i = 0; i < kHostSlots; ++i) BEVK_CUDA(cudaMalloc(&ws.d_dst[i], dst_frame_bytes * chunk));
+        ws.dst_cap = dst_frame_bytes * chunk;
     }
+
+    // From the first enqueue on, every exit -- also an error exit -- first waits for the slot
+    // streams: copies in flight still read / write the caller's host buffers.
+    auto drain = [&ws]() {
+        for (int i = 0; i < kHostSlots; ++i) cudaStreamSynchronize(ws.stream[i]);
+    };
+#define BEVK_CUDA_DRAIN(expr)                                                                       \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            drain();                                                                                \
+            bevk_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return BEVK_E_CUDA;                                                                     \
+        }                                                                                           \
+    } while (0)
 
     int slot = 0;
     for (int f0 = 0; f0 < n_frames; f0 += chunk, slot = (slot + 1) % kHostSlots) {
         const int nf = std::min(chunk, n_frames - f0);
-        cudaStream_t st = g_ws.stream[slot];
+        cudaStream_t st = ws.stream[slot];
         // frames are "rows" of a 2-D copy: pitch = whole frame, width = the referenced row band
-        BEVK_CUDA(cudaMemcpy2DAsync((char *)g_ws.d_src[slot] + r0 * row_bytes, src_frame_bytes,
+        BEVK_CUDA_DRAIN(cudaMemcpy2DAsync((char *)ws.d_src[slot] + r0 * row_bytes, src_frame_bytes,
                                     (const char *)src + (size_t)f0 * src_frame_bytes + r0 * row_bytes,
                                     src_frame_bytes, up_bytes, nf, cudaMemcpyHostToDevice, st));
         std::vector<BevkWarpGroup> groups;
@@ -451,16 +499,17 @@ int bevk_warp_perspective_host(const void *src, void *dst, int n_frames, int src
         build_groups(nf, use_n_mats, idx_ptr, *use_maps, groups);
         WarpArgs ac = a;
         ac.n_frames = nf;
-        rc = run_warp_device(g_ws.d_src[slot], g_ws.d_dst[slot], ac, groups, g_warp_path, st);
+        rc = run_warp_device(ws.d_src[slot], ws.d_dst[slot], ac, groups, g_warp_path, st);
         if (rc) {
-            cudaDeviceSynchronize();
+            drain();
             return rc;
         }
-        BEVK_CUDA(cudaMemcpyAsync((char *)dst + (size_t)f0 * dst_frame_bytes, g_ws.d_dst[slot],
+        BEVK_CUDA_DRAIN(cudaMemcpyAsync((char *)dst + (size_t)f0 * dst_frame_bytes, ws.d_dst[slot],
                                   dst_frame_bytes * nf, cudaMemcpyDeviceToHost, st));
     }
-    for (int i = 0; i < kHostSlots; ++i) BEVK_CUDA(cudaStreamSynchronize(g_ws.stream[i]));
+    for (int i = 0; i < kHostSlots; ++i) BEVK_CUDA_DRAIN(cudaStreamSynchronize(ws.stream[i]));
     return BEVK_OK;
+#undef BEVK_CUDA_DRAIN
 }
 
 }  // extern "C"

@@ -1,7 +1,11 @@
 #!/bin/bash
-# ncu --set full of the staged warp kernel on cfg 2 (after the same command ran clean without ncu)
+# round 2: ncu evidence for the staged warp kernel and the launch list of the bench command
 cd "$(dirname "$0")/.."
-CMD="python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-projection --no-other-configs"
-$CMD > gpurun_out/r2_ncu_plain.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:warp_fast -s 4 -c 1 -o gpurun_out/r2_warp_${1:-a} -f $CMD > gpurun_out/r2_ncu_${1:-a}.log 2>&1
-echo rc=$?; tail -3 gpurun_out/r2_ncu_plain.log | cut -c1-600
+CMD="python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-other-configs"
+$CMD > gpurun_out/r02_plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches.csv $CMD > gpurun_out/r02_ncu_launches.log 2>&1
+echo launches rc=$?
+CMD2="python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-projection --no-other-configs"
+$CMD2 > gpurun_out/r02_plain2.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:warp_fast -s 4 -c 2 -o gpurun_out/r02_warp -f $CMD2 > gpurun_out/r02_ncu_full.log 2>&1
+echo full rc=$?
