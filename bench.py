@@ -35,6 +35,10 @@ WORKLOADS = {
     "cfg5_4k_to_bev2048_f16c3_x64": (64, (3840, 2160), (2048, 2048), 3, "float16", 1, 2, False),
     "cfg5_inv_bev2048_to_4k_u8c3_x64": (64, (2048, 2048), (3840, 2160), 3, "uint8", 1, 2, True),
     "cfg5_inv_bev2048_to_4k_f16c3_x64": (64, (2048, 2048), (3840, 2160), 3, "float16", 1, 2, True),
+    # the cfg-2 map on the other pixel formats of the staged kernel
+    "cfg2_u8c1_x256": (256, (1920, 1080), (1024, 1024), 1, "uint8", 1, 1, False),
+    "cfg2_u8c4_x256": (256, (1920, 1080), (1024, 1024), 4, "uint8", 1, 1, False),
+    "cfg2_f32c3_x128": (128, (1920, 1080), (1024, 1024), 3, "float32", 1, 1, False),
 }
 DEFAULT_WORKLOAD = "cfg2_1080p_to_bev1024_u8c3_bilinear_x256"
 
@@ -535,14 +539,15 @@ def other_configs(dev, steps):
         return e0.elapsed_time(e1) / steps
 
     for wl in ("cfg2_nearest", "cfg5_4k_to_bev2048_u8c3_x64", "cfg5_inv_bev2048_to_4k_u8c3_x64",
-               "cfg5_4k_to_bev2048_f16c3_x64", "cfg5_inv_bev2048_to_4k_f16c3_x64"):
+               "cfg5_4k_to_bev2048_f16c3_x64", "cfg5_inv_bev2048_to_4k_f16c3_x64",
+               "cfg2_u8c1_x256", "cfg2_u8c4_x256", "cfg2_f32c3_x128"):
         n, ssize, dsize, ch, dtype, flags, hscale, inverse = WORKLOADS[wl]
         H = np.linalg.inv(h_canon(hscale)) if inverse else h_canon(hscale)
-        es = 1 if dtype == "uint8" else 2
+        es = {"uint8": 1, "float16": 2, "float32": 4}[dtype]
         g = torch.Generator(device=dev).manual_seed(1234)
         frames = torch.randint(0, 256, (n, ssize[1], ssize[0], ch), dtype=torch.uint8, device=dev, generator=g)
         if dtype != "uint8":
-            frames = (frames.to(torch.float32) / 255.0).to(torch.float16)
+            frames = (frames.to(torch.float32) / 255.0).to(torch.float16 if dtype == "float16" else torch.float32)
         dst = torch.empty((n, dsize[1], dsize[0], ch), dtype=frames.dtype, device=dev)
         T, _, _ = _native.warp_touched_pixels(ssize, dsize, H, flags)
         algo = (T + dsize[0] * dsize[1]) * ch * es * n

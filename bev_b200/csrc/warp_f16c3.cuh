@@ -23,6 +23,7 @@ struct PxF16C3 {
     static constexpr int kBpp = 6;
     static constexpr int kSegBytes = 192;
     static constexpr int kDtype = BEVK_F16;
+    static constexpr int kWinWords = 8;     // window words the kernel keeps per pixel
     static constexpr bool kPairs = false;
     using Reg = PixF16;
     struct Out {
@@ -64,7 +65,7 @@ struct PxF16C3 {
 
     template <bool LINEAR, typename LD>
     static __device__ __forceinline__ void load(const Reg &, uint32_t ra, uint32_t rb, uint32_t last_a,
-                                                uint32_t last_b, uint32_t (&w)[8], LD ld)
+                                                uint32_t last_b, uint32_t (&w)[kWinWords], LD ld)
     {
         w[0] = ld(ra);
         if (LINEAR) {
@@ -92,7 +93,7 @@ struct PxF16C3 {
         return __fmaf_rn(p11, q.w11, r);
     }
     template <bool LINEAR>
-    static __device__ __forceinline__ Out math(const Reg &q, const uint32_t (&w)[8])
+    static __device__ __forceinline__ Out math(const Reg &q, const uint32_t (&w)[kWinWords])
     {
         Out o;
         if (LINEAR) {

@@ -41,6 +41,7 @@
 #include "bevk_common.cuh"
 #include "warp_u8c3.cuh"
 #include "warp_f16c3.cuh"
+#include "warp_formats.cuh"
 
 #include <cuda.h>  // CUtensorMap + enums only; the encoder is fetched through the runtime
 #include <mutex>
@@ -873,7 +874,7 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
                     typename PX::Out P[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        uint32_t w[8];
+                        uint32_t w[PX::kWinWords];
                         const uint32_t a = px[k].addr + sa, b = px[k].addr + sb;
                         PX::template load<LINEAR>(px[k], a, b, a + kLast, b + kLast, w,
                                                   [](uint32_t ad) { return lds32(ad); });
@@ -916,7 +917,7 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
                 typename PX::Out P[4];
                 // all window words of the frame are requested before the first is used: this loop
                 // lives on loads in flight
-                uint32_t w[4][8];
+                uint32_t w[4][PX::kWinWords];
 #pragma unroll
                 for (int k = 0; k < 4; ++k)  // "addresses" are byte offsets inside the frame here
                     PX::template load<LINEAR>(px[k], px[k].addr, px[k].addr + src_row_bytes, last[k],
@@ -1022,12 +1023,35 @@ constexpr int min_ctas(bool linear) { return linear ? BEVK_LINEAR_CTAS : 4; }
 // (cudaFuncSetAttribute is per device), the SM count, the memory-pool set-up.  Guarded by g_map_mutex.
 constexpr int kMaxDevices = 64;
 struct DeviceState {
-    KernelConfig cfg[2][2][3];  // [pixel format: u8x3, f16x3][linear][tile shape: SEGS 4, 2, 1]
+    KernelConfig cfg[5][2][3];  // [pixel format, see format_index][linear][tile shape: SEGS 4, 2, 1]
     int sm_count = 0;
     bool pool_ready = false;
 };
 DeviceState g_dev[kMaxDevices];
 inline int segs_index(int segs) { return segs == 4 ? 0 : (segs == 2 ? 1 : 2); }
+
+// Pixel formats the staged kernel is instantiated for.
+inline int format_index(int dtype, int channels)
+{
+    if (dtype == BEVK_U8) return channels == 3 ? 0 : (channels == 1 ? 2 : (channels == 4 ? 3 : -1));
+    if (dtype == BEVK_F16) return channels == 3 ? 1 : -1;
+    if (dtype == BEVK_F32) return channels == 3 ? 4 : -1;
+    return -1;
+}
+template <typename F> auto with_format(int fmt, F f)
+{
+    switch (fmt) {
+    case 1: return f(PxF16C3());
+    case 2: return f(PxU8C1());
+    case 3: return f(PxU8C4());
+    case 4: return f(PxF32C3());
+    default: return f(PxU8C3());
+    }
+}
+inline int format_bpp(int fmt)
+{
+    return with_format(fmt, [](auto px) { return (int)decltype(px)::kBpp; });
+}
 
 template <typename PX, bool LINEAR, int SEGS> int configure(KernelConfig &cfg)
 {
@@ -1229,12 +1253,13 @@ int pick_tile_shape(const BevkWarpParams &p, int linear, int bpp, int ring_bytes
 int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, int linear, int force,
                           cudaStream_t stream)
 {
-    // qualification: uint8 x 3 or float16 x 3, zero border, rows the tensor maps / word stores
-    // can address, per-frame dst pointer steps that fit 32 bits
-    if (channels != 3 || (dtype != BEVK_U8 && dtype != BEVK_F16)) return 0;
-    const int fmt = dtype == BEVK_F16 ? 1 : 0;
-    const int bpp = fmt ? PxF16C3::kBpp : PxU8C3::kBpp;
-    if (p_in.border[0] != 0.f || p_in.border[1] != 0.f || p_in.border[2] != 0.f) return 0;
+    // qualification: a pixel format the kernel is instantiated for, zero border, rows the tensor
+    // maps / word stores can address, per-frame dst pointer steps that fit 32 bits
+    const int fmt = format_index(dtype, channels);
+    if (fmt < 0) return 0;
+    const int bpp = format_bpp(fmt);
+    for (int c = 0; c < channels; ++c)
+        if (p_in.border[c] != 0.f) return 0;
     if (p_in.src_w < 2 || p_in.src_h < 2) return 0;
     if ((p_in.src_w * bpp) % 16 != 0 || (p_in.dst_w % 4) != 0) return 0;
     if (((uintptr_t)p_in.src % 16) != 0 || ((uintptr_t)p_in.dst % 4) != 0) return 0;
@@ -1242,7 +1267,7 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
     BevkWarpParams p = p_in;
     int n_src_frames = 0, max_count = 0;
     for (int i = 0; i < p.n_groups; ++i)
-        if ((long long)p.g[i].stride * p.dst_frame_elems * (fmt ? 2 : 1) > 0xffffffffLL || p.g[i].stride < 1)
+        if ((long long)p.g[i].stride * p.dst_frame_elems * (bpp / channels) > 0xffffffffLL || p.g[i].stride < 1)
             return 0;
     for (int i = 0; i < p.n_groups; ++i) {
         const int last = p.g[i].first + (p.g[i].count - 1) * p.g[i].stride;
@@ -1276,7 +1301,7 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
         // tile shape: every shape's kernel has the same ring size, so configure the widest first
         KernelConfig &c0 = ds.cfg[fmt][linear ? 1 : 0][0];
         if (!c0.ready) {
-            int rc = fmt ? configure_any<PxF16C3>(linear, 4, c0) : configure_any<PxU8C3>(linear, 4, c0);
+            int rc = with_format(fmt, [&](auto px) { return configure_any<decltype(px)>(linear, 4, c0); });
             if (rc) return rc;
         }
         cfg0 = c0;
@@ -1288,7 +1313,7 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
         std::lock_guard<std::mutex> lock(g_map_mutex);
         KernelConfig &c = ds.cfg[fmt][linear ? 1 : 0][segs_index(segs)];
         if (!c.ready) {
-            int rc = fmt ? configure_any<PxF16C3>(linear, segs, c) : configure_any<PxU8C3>(linear, segs, c);
+            int rc = with_format(fmt, [&](auto px) { return configure_any<decltype(px)>(linear, segs, c); });
             if (rc) return rc;
         }
         cfg = c;
@@ -1391,12 +1416,11 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
     int rc2 = 0;
     if (e == cudaSuccess) {
         const int smem = cfg.ring_bytes + kBarBytes + kTailSlack;
-        if (fmt)
-            launch_any<PxF16C3>(linear, segs, grid, smem, stream, p, maps, plan, tiles_x, tiles_y, (int)items,
-                                cfg.ring_bytes, sc);
-        else
-            launch_any<PxU8C3>(linear, segs, grid, smem, stream, p, maps, plan, tiles_x, tiles_y, (int)items,
-                               cfg.ring_bytes, sc);
+        with_format(fmt, [&](auto px) {
+            launch_any<decltype(px)>(linear, segs, grid, smem, stream, p, maps, plan, tiles_x, tiles_y, (int)items,
+                                     cfg.ring_bytes, sc);
+            return 0;
+        });
         e = cudaGetLastError();
         if (e == cudaSuccess && split) {
             // the tiles the staged kernel marked, through the direct-gather kernel (same stream)

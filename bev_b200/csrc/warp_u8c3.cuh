@@ -87,6 +87,7 @@ struct PxU8C3 {
     static constexpr int kBpp = 3;         // bytes per pixel
     static constexpr int kSegBytes = 96;   // bytes of a 32-pixel row segment
     static constexpr int kDtype = BEVK_U8;
+    static constexpr int kWinWords = 8;     // window words the kernel keeps per pixel
     static constexpr bool kPairs = true;   // the staged kernel's shared-window pair path exists for this format
     using Reg = Pix;
     using Out = uint32_t;                  // [c0, c1, c2, 0]
@@ -131,7 +132,7 @@ struct PxU8C3 {
 
     template <bool LINEAR, typename LD>
     static __device__ __forceinline__ void load(const Reg &q, uint32_t ra, uint32_t rb, uint32_t last_a,
-                                                uint32_t last_b, uint32_t (&w)[8], LD ld)
+                                                uint32_t last_b, uint32_t (&w)[kWinWords], LD ld)
     {
         // ra / rb: address of the first window word in row 0 / 1; last_a / last_b: address of the
         // last word of each row (ra + 8 unless the caller had to clamp it)
@@ -151,7 +152,7 @@ struct PxU8C3 {
         }
     }
     template <bool LINEAR>
-    static __device__ __forceinline__ Out math(const Reg &q, const uint32_t (&w)[8])
+    static __device__ __forceinline__ Out math(const Reg &q, const uint32_t (&w)[kWinWords])
     {
         if (LINEAR)  // byte-align the window of both rows, then interpolate
             return lerp_aligned(q, __funnelshift_r(w[0], w[1], q.sh), __funnelshift_r(w[1], w[2], q.sh),

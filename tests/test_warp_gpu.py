@@ -440,3 +440,32 @@ def test_concurrent_streams_and_threads():
     for tid in results:
         for j, o in results[tid]:
             assert torch.equal(o, serial[j]), (tid, j)
+
+
+@pytest.mark.parametrize("dtype,ch", [("uint8", 1), ("uint8", 4), ("float32", 3), ("uint8", 3), ("float16", 3)])
+@pytest.mark.parametrize("flags", [1, 0, 17, 16])
+def test_staged_kernel_pixel_formats(dtype, ch, flags):
+    """Every pixel-format policy of the staged (TMA) kernel, forced: uint8 x 1 / x 3 / x 4, float16 x 3,
+    float32 x 3, bilinear and nearest, forward and WARP_INVERSE_MAP, over maps that magnify, minify and
+    leave the source (zero border): bit-identical to the oracle (float32 negative values included)."""
+    rng = np.random.default_rng(17 * ch + flags)
+    n = 6
+    frames = np.stack([util.seeded_frame(5000 + 7 * ch + i, 270, 480, ch, dtype) for i in range(n)])
+    if dtype == "float32":
+        frames = frames * 2.0 - 1.0  # signed values: sums of products in cv2's order, signs of zero
+        frames = frames.astype(np.float32)
+    quad = np.array([[0, 0], [479, 0], [479, 269], [0, 269]], np.float64)
+    cases = [((256, 256), 30.0), ((64, 48), 5.0), ((800, 600), 40.0), ((160, 400), 90.0)]
+    for (dw, dh), jitter in cases:
+        d = np.array([[0, 0], [dw - 1, 0], [dw - 1, dh - 1], [0, dh - 1]], np.float64)
+        H = homo.homo_from_pts(quad + rng.normal(size=(4, 2)) * jitter, d)
+        if flags & 16:
+            H = np.linalg.inv(H)
+        t = torch.from_numpy(frames).to(DEV)
+        out = homo.warp_perspective(t, H, (dw, dh), flags=flags, path="fast").cpu().numpy()
+        gen = homo.warp_perspective(t, H, (dw, dh), flags=flags, path="generic").cpu().numpy()
+        assert util.bits_equal(out, gen), (dtype, ch, flags, dw, dh, "staged vs direct-gather kernels")
+        for i in (0, n - 1):
+            ref = wo.warp_perspective(frames[i] if ch > 1 else frames[i][:, :, 0], H, (dw, dh), flags=flags)
+            got = out[i] if ch > 1 else out[i][:, :, 0]
+            assert util.bits_equal(got, ref), (dtype, ch, flags, dw, dh, i)
