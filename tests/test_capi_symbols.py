@@ -93,3 +93,17 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), fn
                 assert "libbevoracle" not in text, fn
+
+
+def test_torch_extension_loads_and_registers_the_operators():
+    """The thin PyTorch C++ extension: loads on a machine without a GPU, registers
+    torch.ops.bev_cuda.* with a CUDA implementation only (CPU tensors fail in the dispatcher)."""
+    import pytest
+    import torch
+    from bev_b200 import torch_ops
+    torch_ops.load()
+    for name in ("warp_perspective", "project_points", "rbox_corners_project", "corners_to_rbox",
+                 "rbox_similarity"):
+        assert hasattr(torch.ops.bev_cuda, name), name
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        torch.ops.bev_cuda.project_points(torch.zeros((3, 2)), torch.eye(3, dtype=torch.float64))
