@@ -137,8 +137,6 @@ struct WarpScratch {
     int pf;           // L2 prefetch distance in stages beyond the fills (-1: depth-2 rings only, 2 stages)
     int pf1;          // the same for depth-2 rings when pf < 0
     int max_fps;      // frames per ring stage, at most
-    int row_major;    // walk the tiles row by row instead of column by column
-    int y_group, y_stride;  // tile rows are walked in groups of y_group, group g at (g * y_stride) % n_groups
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -357,16 +355,27 @@ __device__ __forceinline__ uint32_t stage_loop(const LoopCtx &c, uint32_t use, u
 // thread pixel k = 2 j + i is row i of vertical PAIR j: the two pixels of a pair are vertical
 // neighbours, so wherever the map magnifies vertically their 2x2 source windows overlap and the
 // pair path below loads the window rows once for both.
-template <int SEGS> __device__ __forceinline__ int warp_px_x(int warp)
+// (PAIRS = the kernel has the pair path, i.e. uint8 x 3 bilinear.)  Kernels without it keep each
+// warp on ONE dst row where the tile is wide enough -- 4 / 2 / 1 segments of 32 pixels in a row --
+// so that a warp writes the longest contiguous run the tile offers.
+template <int SEGS, bool PAIRS> __device__ __forceinline__ int warp_px_x(int warp)
 {
+    if (!PAIRS) return 0;
     return SEGS >= 2 ? 64 * (warp % (SEGS >= 2 ? SEGS / 2 : 1)) : 0;
 }
-template <int SEGS> __device__ __forceinline__ int warp_px_y(int warp)
+template <int SEGS, bool PAIRS> __device__ __forceinline__ int warp_px_y(int warp)
 {
+    if (!PAIRS) return warp * (4 / SEGS);
     return SEGS >= 2 ? 2 * (warp / (SEGS >= 2 ? SEGS / 2 : 1)) : 4 * warp;
 }
-template <int SEGS> __device__ __forceinline__ constexpr int px_seg(int k) { return SEGS >= 2 ? (k >> 1) : 0; }
-template <int SEGS> __device__ __forceinline__ constexpr int px_row(int k) { return SEGS >= 2 ? (k & 1) : k; }
+template <int SEGS, bool PAIRS> __device__ __forceinline__ constexpr int px_seg(int k)
+{
+    return PAIRS ? (SEGS >= 2 ? (k >> 1) : 0) : k % SEGS;
+}
+template <int SEGS, bool PAIRS> __device__ __forceinline__ constexpr int px_row(int k)
+{
+    return PAIRS ? (SEGS >= 2 ? (k & 1) : k) : k / SEGS;
+}
 
 // Frame-invariant registers of a vertical pixel pair that shares its window loads (uint8 x 3,
 // bilinear).  `first` is the pixel whose window starts on the pair's first source row; the second
@@ -471,6 +480,7 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
     const uint8_t *src = (const uint8_t *)p.src;
     uint8_t *dst = (uint8_t *)p.dst;
     constexpr int kBpp = PX::kBpp;
+    constexpr bool kPairMap = LINEAR && PX::kPairs;  // which dst pixels a thread owns (see warp_px_x)
     const int src_row_bytes = p.src_w * kBpp;
     const long long src_frame_bytes = (long long)src_row_bytes * p.src_h;
     const long long dst_frame_bytes = (long long)p.dst_w * p.dst_h * kBpp;
@@ -488,18 +498,8 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
         // column-major walk: concurrently running CTAs cover whole tile columns, i.e. both the
         // magnified far field (store-heavy) and the minified near field (load-heavy)
         o.gi = gi;
-        int ty;
-        if (sc.row_major) {
-            ty = tile / tiles_x;
-            o.tile_x = tile - ty * tiles_x;
-        } else {
-            o.tile_x = tile / tiles_y;
-            ty = tile - o.tile_x * tiles_y;
-        }
-        // ... with the tile rows of a column permuted by a stride, so that the CTAs that share an
-        // SM (consecutive items) work on different zones of the map at any time
-        const int yg = ty / sc.y_group;
-        o.tile_y = (int)(((long long)yg * sc.y_stride) % (tiles_y / sc.y_group)) * sc.y_group + (ty - yg * sc.y_group);
+        o.tile_x = tile / tiles_y;
+        o.tile_y = tile - o.tile_x * tiles_y;
         const int count = p.g[gi].count;
         o.f0 = (int)(((unsigned long long)count * plan.cum[chunk]) >> 16);
         o.n_frames = (int)(((unsigned long long)count * plan.cum[chunk + 1]) >> 16) - o.f0;
@@ -532,8 +532,8 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
         const int g_first = s_item[par].first, g_stride = s_item[par].stride;
         const int chunk = s_item[par].chunk;
         const bool published = s_item[par].ready != 0;
-        const int x0 = tile_x * tile_w(SEGS) + warp_px_x<SEGS>(warp);
-        const int y0 = tile_y * tile_h(SEGS) + warp_px_y<SEGS>(warp);
+        const int x0 = tile_x * tile_w(SEGS) + warp_px_x<SEGS, kPairMap>(warp);
+        const int y0 = tile_y * tile_h(SEGS) + warp_px_y<SEGS, kPairMap>(warp);
         const int tile_id = gi * n_tiles + tile_x * tiles_y + tile_y;
         par ^= 1;
 
@@ -548,7 +548,7 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
             bx1 = by1 = -1;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const int x = x0 + lane + 32 * px_seg<SEGS>(k), y = y0 + px_row<SEGS>(k);
+                const int x = x0 + lane + 32 * px_seg<SEGS, kPairMap>(k), y = y0 + px_row<SEGS, kPairMap>(k);
                 const bool in_dst = (x < p.dst_w) && (y < p.dst_h);
                 int X, Y, wc0, wc1, wr0, wr1;
                 const int xc = min(x, p.dst_w - 1);
@@ -707,14 +707,14 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             // pixels left in this 32-pixel segment: a multiple of 4 (dst_w % 4 == 0)
-            const int valid_px = min(32, p.dst_w - (x0 + 32 * px_seg<SEGS>(k)));
-            seg_ok[k] = (y0 + px_row<SEGS>(k) < p.dst_h) && PX::lane_stores(lane, valid_px);
+            const int valid_px = min(32, p.dst_w - (x0 + 32 * px_seg<SEGS, kPairMap>(k)));
+            seg_ok[k] = (y0 + px_row<SEGS, kPairMap>(k) < p.dst_h) && PX::lane_stores(lane, valid_px);
         }
         // where pixel k's segment goes, from the thread's pointer into dst row y0 (dd) and the one
         // into row y0 + 1 (dd1): compile-time segment offsets, one runtime row step
         auto seg_ptr = [row_bytes](uint8_t *dd, uint8_t *dd1, int k) -> uint8_t * {
-            if (SEGS >= 2) return (px_row<SEGS>(k) ? dd1 : dd) + PX::kSegBytes * px_seg<SEGS>(k);
-            return (k & 1 ? dd1 : dd) + (k >> 1) * 2 * (size_t)row_bytes;
+            const int row = px_row<SEGS, kPairMap>(k), seg = px_seg<SEGS, kPairMap>(k);
+            return (row & 1 ? dd1 : dd) + (row >> 1) * 2 * (size_t)row_bytes + PX::kSegBytes * seg;
         };
         if (kExperiments && (sc.dbg & 1)) seg_ok[0] = seg_ok[1] = seg_ok[2] = seg_ok[3] = false;
         uint32_t d_step = (uint32_t)g_stride * (uint32_t)dst_frame_bytes;  // < 2^32 (host check)
@@ -1366,7 +1366,12 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
     // other threads get their own): [item counter | split flags | set-up ready flags] zeroed, then
     // the tiles' set-up headers and records.
     split = split && !getenv("BEVK_NO_SPLIT");  // env: tuning aid
-    const bool share_setup = plan.n_chunks > 1 && tile_groups * kRecWords * kThreads * 4 <= (512LL << 20) &&
+    // Sharing a tile's set-up between its frame chunks pays where the set-up is expensive and the
+    // issue slots are the scarce resource: uint8 x 3 bilinear (cfg 2: 0.444 -> 0.428 ms).  The
+    // other kernels have issue slots to spare and lose a little to the extra round trips (nearest
+    // 0.326 -> 0.331 ms), so they recompute.
+    const bool share_setup = fmt == 0 && linear && plan.n_chunks > 1 &&
+                             tile_groups * kRecWords * kThreads * 4 <= (512LL << 20) &&
                              !getenv("BEVK_NO_SETUP_CACHE");
     const size_t off_hard = 256;
     const size_t off_ready = off_hard + (((size_t)(split ? tile_groups : 0) + 255) & ~(size_t)255);
@@ -1386,24 +1391,7 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
     sc.slack = getenv("BEVK_SLACK") ? atoi(getenv("BEVK_SLACK")) : 0;
     sc.pf = getenv("BEVK_PF") ? atoi(getenv("BEVK_PF")) : -1;
     sc.pf1 = getenv("BEVK_PF1") ? atoi(getenv("BEVK_PF1")) : kPrefetchAhead;
-    sc.row_major = getenv("BEVK_ROWMAJOR") ? atoi(getenv("BEVK_ROWMAJOR")) : 0;
     sc.max_fps = getenv("BEVK_MAXFPS") ? atoi(getenv("BEVK_MAXFPS")) : kMaxStageFrames;
-    {
-        // stride permutation of the tile rows: groups of y_group adjacent rows stay together (their
-        // source boxes overlap and are re-served by L2), the groups are visited ~3/8 of a column apart
-        int g = getenv("BEVK_YGROUP") ? atoi(getenv("BEVK_YGROUP")) : 0;
-        if (g < 1 || tiles_y % g != 0) g = 0;
-        sc.y_group = g ? g : 1;
-        const int n = tiles_y / sc.y_group;
-        int st = 1;
-        if (g) {
-            st = (3 * n) / 8;
-            if (st < 1) st = 1;
-            auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
-            while (gcd(st, n) != 1) ++st;
-        }
-        sc.y_stride = st;
-    }
     if (split) {
         // one byte per (group, tile): the staged kernel marks the tiles it leaves to the second launch
         p.hard = scratch + off_hard;

@@ -138,15 +138,11 @@ struct PxU8C3 {
         // last word of each row (ra + 8 unless the caller had to clamp it)
         w[0] = ld(ra);
         if (LINEAR) {
-            // a 6-byte window row reaches into a third word only when it starts on byte 3; where
-            // the lanes' windows are spread over many banks (minifying maps) the lanes that skip
-            // the load save shared-memory wavefronts
-            const bool third = q.sh == 24;
             w[1] = ld(ra + 4);
-            w[2] = third ? ld(last_a) : 0u;
+            w[2] = ld(last_a);
             w[3] = ld(rb);
             w[4] = ld(rb + 4);
-            w[5] = third ? ld(last_b) : 0u;
+            w[5] = ld(last_b);
         } else {
             w[1] = ld(last_a);
         }
