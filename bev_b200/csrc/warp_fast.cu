@@ -131,6 +131,7 @@ struct WarpScratch {
     int *ready;       // [groups * tiles], zeroed; NULL: every item computes its own set-up
     int *hdr;         // [groups * tiles][kHdrInts]
     uint32_t *rec;    // [groups * tiles][kRecWords][kThreads]
+    uint32_t recip_per_chunk, recip_tiles, recip_tiles_y;  // ceil(2^32 / d) for the item decode
     int no_pairs;     // tuning aid (BEVK_NO_PAIRS): every warp takes the per-pixel path
     int dbg;          // -DBEVK_EXPERIMENTS builds only (BEVK_DBG): 1 = no stores, 2 = no TMA traffic / waits
     int slack;        // ring stages NOT in flight ahead of the consumers (0: half the ring)
@@ -308,17 +309,22 @@ __device__ __forceinline__ void feed(const LoopCtx &c, int done, uint32_t use, i
 // slower warp to release it).  body(sa, d, release) interpolates the thread's pixels of ONE frame
 // staged at shared address sa into d; it calls release() once all its shared-memory reads are
 // issued.  Returns the advanced stage counter.
-template <typename BODY>
+// started() is run by thread 0 once the first copies of the item are on their way (the decode of
+// the CTA's next item: thread-0 work that would otherwise delay every item's first bytes).
+template <typename BODY, typename STARTED>
 __device__ __forceinline__ uint32_t stage_loop(const LoopCtx &c, uint32_t use, uint8_t *d,
-                                               const uint32_t d_step, const int tid, BODY body)
+                                               const uint32_t d_step, const int tid, BODY body, STARTED started)
 {
     const uint32_t smask = (1u << c.slog) - 1u;
     const int lane = tid & 31, warp = tid >> 5;
-    if (tid == 0 && !(kExperiments && (c.dbg & 2))) {
-        for (int s = 0; s < c.ahead && s * c.fps < c.n_frames; ++s)
-            produce<true>(c.plan, c.maps, s * c.fps, use + s);
-        for (int s = c.ahead; s < c.ahead + c.pf && s * c.fps < c.n_frames; ++s)
-            produce<false>(c.plan, c.maps, s * c.fps, 0);
+    if (tid == 0) {
+        if (!(kExperiments && (c.dbg & 2))) {
+            for (int s = 0; s < c.ahead && s * c.fps < c.n_frames; ++s)
+                produce<true>(c.plan, c.maps, s * c.fps, use + s);
+            for (int s = c.ahead; s < c.ahead + c.pf && s * c.fps < c.n_frames; ++s)
+                produce<false>(c.plan, c.maps, s * c.fps, 0);
+        }
+        started();
     }
     int done = 0;
 #pragma unroll 1
@@ -490,15 +496,23 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
     // yet never holds a tile's first chunk while others wait for its set-up.  Thread 0 decodes an
     // item (integer divisions, parameter reads) one item ahead of its use.
     const int per_chunk = p.n_groups * n_tiles;
+    // n / d for n < 2^31 with the host's reciprocal ceil(2^32 / d): one multiply and a fix-up
+    // instead of an integer division (the decode runs on one thread, every cycle of it delays warp 0)
+    auto fast_div = [](int n, int d, uint32_t recip) {
+        uint32_t q = __umulhi((uint32_t)n, recip);
+        if (q * (uint32_t)d > (uint32_t)n) --q;          // ceil() made the quotient one too large
+        if ((q + 1u) * (uint32_t)d <= (uint32_t)n) ++q;  // d == 1: the reciprocal saturates at 2^32 - 1
+        return (int)q;
+    };
     auto decode = [&](int item, ItemDesc &o) {
         o.item = item;
         if (item >= total_items) return;
-        const int chunk = item / per_chunk, rem = item - chunk * per_chunk;
-        const int gi = rem / n_tiles, tile = rem - gi * n_tiles;
+        const int chunk = fast_div(item, per_chunk, sc.recip_per_chunk), rem = item - chunk * per_chunk;
+        const int gi = fast_div(rem, n_tiles, sc.recip_tiles), tile = rem - gi * n_tiles;
         // column-major walk: concurrently running CTAs cover whole tile columns, i.e. both the
         // magnified far field (store-heavy) and the minified near field (load-heavy)
         o.gi = gi;
-        o.tile_x = tile / tiles_y;
+        o.tile_x = fast_div(tile, tiles_y, sc.recip_tiles_y);
         o.tile_y = tile - o.tile_x * tiles_y;
         const int count = p.g[gi].count;
         o.f0 = (int)(((unsigned long long)count * plan.cum[chunk]) >> 16);
@@ -506,6 +520,7 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
         o.first = p.g[gi].first;
         o.stride = p.g[gi].stride;
         o.chunk = chunk;
+        // one item ahead of its use: by then the first chunk's CTA has nearly always published
         // one item ahead of its use: by then the first chunk's CTA has nearly always published
         o.ready = (sc.ready != nullptr && chunk > 0)
                       ? ld_acquire(sc.ready + (gi * n_tiles + o.tile_x * tiles_y + o.tile_y))
@@ -532,6 +547,10 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
         const int g_first = s_item[par].first, g_stride = s_item[par].stride;
         const int chunk = s_item[par].chunk;
         const bool published = s_item[par].ready != 0;
+        // the index of the CTA's NEXT item: requested now, needed only once this item's first
+        // copies are in flight (next_item_decode below), so the atomic's round trip costs nothing
+        int next_raw = 0;
+        if (tid == 0) next_raw = atomicAdd(sc.next_item, 1);
         const int x0 = tile_x * tile_w(SEGS) + warp_px_x<SEGS, kPairMap>(warp);
         const int y0 = tile_y * tile_h(SEGS) + warp_px_y<SEGS, kPairMap>(warp);
         const int tile_id = gi * n_tiles + tile_x * tiles_y + tile_y;
@@ -692,13 +711,13 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
         if (tid == 0) {
             // the tile's set-up is in global memory (every thread fenced its part before the barrier)
             if (sc.ready != nullptr && chunk == 0) st_release(sc.ready + tile_id, 1);
-            // re-arm the box for the next item (its first atomics come after this item's last
-            // barrier), then fetch + decode the next item: nobody waits for thread 0 until then
+            // re-arm the box for the next item (its first atomics come after this item's last barrier)
             s_box[0] = s_box[2] = 1 << 30;
             s_box[1] = s_box[3] = -1;
             s_any = 0;
-            decode(atomicAdd(sc.next_item, 1), s_item[par]);
         }
+        // thread 0, once this item's first copies are issued (or at once where nothing is staged)
+        auto next_item_decode = [&]() { decode(next_raw, s_item[par]); };
 
         // ---- store geometry ---------------------------------------------------------------------
         // which words of a 32-pixel row segment this lane writes is the pixel format's business
@@ -722,6 +741,7 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
         uint8_t *d = dst + (long long)(g_first + f0 * g_stride) * dst_frame_bytes +
                      ((long long)y0 * p.dst_w + x0) * kBpp + PX::lane_offset(lane);
 
+        if ((!any || !staged) && tid == 0) next_item_decode();
         if (!any) {
             // whole tile maps outside the source: constant border (0) for every frame
 #pragma unroll 1
@@ -833,7 +853,7 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
                             PX::store(seg_ptr(dd, dd, 2 * j), P[2 * j], (ok >> (2 * j)) & 1u, st, lane);
                             PX::store(seg_ptr(ds, ds, 2 * j), P[2 * j + 1], (ok >> (2 * j + 1)) & 1u, st, lane);
                         }
-                    });
+                    }, next_item_decode);
                 } else {
                     use = stage_loop(c, use, d_first, d_step, tid, [&](uint32_t sa, uint8_t *dd, auto release) {
                         const uint32_t sb = sa + c.pitch, sc2 = sb + c.pitch;
@@ -855,7 +875,7 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
                             PX::store(seg_ptr(dd, dd, 2 * j), P[2 * j], (ok >> (2 * j)) & 1u, st, lane);
                             PX::store(seg_ptr(ds, ds, 2 * j), P[2 * j + 1], (ok >> (2 * j + 1)) & 1u, st, lane);
                         }
-                    });
+                    }, next_item_decode);
                 }
             }
             if (var == 3) {
@@ -884,7 +904,7 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
                     // pack the lanes' pixels into words and store coalesced row segments
 #pragma unroll
                     for (int k = 0; k < 4; ++k) PX::store(seg_ptr(dd, dd + row_bytes, k), P[k], seg_ok[k], st, lane);
-                });
+                }, next_item_decode);
             }
             __syncthreads();  // every warp has read s_use and left the ring
             if (tid == 0) s_use[slog - 1] = use;
@@ -1386,6 +1406,10 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
     sc.ready = share_setup ? (int *)(scratch + off_ready) : nullptr;
     sc.hdr = share_setup ? (int *)(scratch + off_hdr) : nullptr;
     sc.rec = share_setup ? (uint32_t *)(scratch + off_rec) : nullptr;
+    auto recip = [](long long d) { return d <= 1 ? 0xffffffffu : (uint32_t)(((1ULL << 32) + d - 1) / d); };
+    sc.recip_per_chunk = recip(tile_groups);
+    sc.recip_tiles = recip(n_tiles);
+    sc.recip_tiles_y = recip(tiles_y);
     sc.no_pairs = getenv("BEVK_NO_PAIRS") ? 1 : 0;
     sc.dbg = (kExperiments && getenv("BEVK_DBG")) ? atoi(getenv("BEVK_DBG")) : 0;
     sc.slack = getenv("BEVK_SLACK") ? atoi(getenv("BEVK_SLACK")) : 0;
