@@ -469,3 +469,35 @@ def test_staged_kernel_pixel_formats(dtype, ch, flags):
             ref = wo.warp_perspective(frames[i] if ch > 1 else frames[i][:, :, 0], H, (dw, dh), flags=flags)
             got = out[i] if ch > 1 else out[i][:, :, 0]
             assert util.bits_equal(got, ref), (dtype, ch, flags, dw, dh, i)
+
+
+def test_pair_path_orientations():
+    """The shared-window pair path of the staged uint8 x 3 bilinear kernel has three row patterns
+    (both pixels of a vertical pair on the same source rows, the lower dst pixel one source row
+    further down, or -- maps that flip the image vertically -- one row further up) and per-pixel
+    column offsets to either side.  Magnifying maps in all eight orientations (flips, transposes,
+    rotations, with shear so that columns drift both ways) must stay bit-exact."""
+    frames = np.stack([util.seeded_frame(6000 + i, 270, 480, 3, "uint8") for i in range(5)])
+    t = torch.from_numpy(frames).to(DEV)
+    W, Hh = 480.0, 270.0
+    base = [
+        np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1.0]]),                 # upright
+        np.array([[1, 0, 0], [0, -1, Hh - 1], [0, 0, 1.0]]),           # vertical flip   -> row step -1
+        np.array([[-1, 0, W - 1], [0, 1, 0], [0, 0, 1.0]]),            # horizontal flip -> column step -1
+        np.array([[-1, 0, W - 1], [0, -1, Hh - 1], [0, 0, 1.0]]),      # rotation by 180 degrees
+        np.array([[0, 1, 0], [1, 0, 0], [0, 0, 1.0]]),                 # transpose
+        np.array([[0, -1, Hh - 1], [1, 0, 0], [0, 0, 1.0]]),           # rotation by 90 degrees
+    ]
+    for bi, B in enumerate(base):
+        for zoom, shear, persp in ((3.7, 0.35, 1.0), (1.6, -0.5, 1.0), (6.0, 0.0, 1.0), (4.3, 0.0, 0.0),
+                                   (2.2, 0.0, 0.0)):
+            # persp = 0, shear = 0: every dst row maps to ONE source row, so whole warps share a row
+            # pattern (the warp-uniform variants of the pair path); the others mix patterns in a warp
+            Z = np.array([[zoom * 0.9, shear, 3.0], [shear * 0.4, zoom, -5.0],
+                          [1e-5 * persp, 2e-5 * persp, 1.0]])
+            H = Z @ B
+            dsize = (512, 384)
+            out = homo.warp_perspective(t, H, dsize, flags=1, path="fast").cpu().numpy()
+            for i in (0, 4):
+                ref = wo.warp_perspective(frames[i], H, dsize, flags=1)
+                assert util.bits_equal(out[i], ref), (bi, zoom, shear, persp, i)
