@@ -50,7 +50,14 @@
 
 namespace {
 
-constexpr int kThreads = 256, kWarps = kThreads / 32;
+// CTA size: 4 warps (tiles of 512 pixels), 6 CTAs per SM for the 80-register kernels.  8 warps / 3 CTAs
+// hold the same registers and ring bytes per SM, but twice as many independent CTAs hide each
+// other's item boundaries (barrier skew, set-up, first TMA round trip) better: cfg 2 0.421 -> 0.415 ms,
+// cfg 5 0.453 -> 0.435 ms.
+#ifndef BEVK_CTA_THREADS
+#define BEVK_CTA_THREADS 128
+#endif
+constexpr int kThreads = BEVK_CTA_THREADS, kWarps = kThreads / 32;
 // Tile shapes.  A CTA always owns 1024 dst pixels, 4 per thread; SEGS = 32-pixel segments per tile
 // row: 4 -> 128x8 (warp w owns tile row w), 2 -> 64x16 (rows 2w, 2w+1), 1 -> 32x32 (rows 4w..4w+3).
 // Narrower tiles bound the width of the source box where the map minifies horizontally.
@@ -67,7 +74,7 @@ constexpr int kNarrowW = 12, kNarrowH = 16, kWideW = 4, kWideH = 8;
 constexpr int kMapCount = kNarrowW * kNarrowH + kWideW * kWideH;
 constexpr int kMaxBoxWidth = 2048, kMaxBoxHeight = 32;
 constexpr int kMaxBoxes = 3;
-constexpr int kMaxStageFrames = 4;              // frames that share one ring stage / mbarrier phase
+constexpr int kMaxStageFrames = 8;              // frames that share one ring stage / mbarrier phase
 constexpr int kBarBytes = 256;                  // 28 mbarriers: ring depths 2, 4 and 8
 constexpr int kPrefetchAhead = 2;               // depth-2 rings: L2 prefetch runs this many stages ahead
 #ifdef BEVK_EXPERIMENTS
@@ -1038,7 +1045,7 @@ struct KernelConfig {
 #ifndef BEVK_LINEAR_CTAS
 #define BEVK_LINEAR_CTAS 3
 #endif
-constexpr int min_ctas(bool linear) { return linear ? BEVK_LINEAR_CTAS : 4; }
+constexpr int min_ctas(bool linear) { return (linear ? BEVK_LINEAR_CTAS : 4) * (256 / kThreads); }
 // Everything that belongs to one device: the kernels' shared-memory opt-in and ring size
 // (cudaFuncSetAttribute is per device), the SM count, the memory-pool set-up.  Guarded by g_map_mutex.
 constexpr int kMaxDevices = 64;
