@@ -23,6 +23,7 @@ struct PxF16C3 {
     static constexpr int kBpp = 6;
     static constexpr int kSegBytes = 192;
     static constexpr int kDtype = BEVK_F16;
+    static constexpr int kLinearThreads = 128, kNearestThreads = 256;  // CTA size of the staged kernel (warp_fast.cu)
     static constexpr int kWinWords = 8;     // window words the kernel keeps per pixel
     static constexpr bool kPairs = false;
     using Reg = PixF16;

@@ -50,19 +50,21 @@
 
 namespace {
 
-// CTA size: 4 warps (tiles of 512 pixels), 6 CTAs per SM for the 80-register kernels.  8 warps / 3 CTAs
-// hold the same registers and ring bytes per SM, but twice as many independent CTAs hide each
-// other's item boundaries (barrier skew, set-up, first TMA round trip) better: cfg 2 0.421 -> 0.415 ms,
-// cfg 5 0.453 -> 0.435 ms.
-#ifndef BEVK_CTA_THREADS
-#define BEVK_CTA_THREADS 128
-#endif
-constexpr int kThreads = BEVK_CTA_THREADS, kWarps = kThreads / 32;
+// CTA size is a property of the kernel (pixel format x interpolation, see cta_threads below): 4 warps
+// (tiles of 512 pixels, 6 CTAs per SM for the 80-register kernels) or 8 warps (1024 pixels, 3 CTAs).
+// Both hold the same registers and ring bytes per SM; twice as many independent CTAs hide each
+// other's item boundaries (barrier skew, set-up, first TMA round trip) better where the boxes are
+// narrow -- uint8 x 3 bilinear: cfg 2 0.421 -> 0.411 ms, cfg 5 0.453 -> 0.436 ms, float16 0.90 ->
+// 0.86 ms -- while 4-byte pixels (0.465 -> 0.509 ms) and nearest (+2 %) do better with the taller tile.
+template <typename PX, bool LINEAR> constexpr int cta_threads()
+{
+    return LINEAR ? PX::kLinearThreads : PX::kNearestThreads;
+}
 // Tile shapes.  A CTA always owns 1024 dst pixels, 4 per thread; SEGS = 32-pixel segments per tile
 // row: 4 -> 128x8 (warp w owns tile row w), 2 -> 64x16 (rows 2w, 2w+1), 1 -> 32x32 (rows 4w..4w+3).
 // Narrower tiles bound the width of the source box where the map minifies horizontally.
 __host__ __device__ constexpr int tile_w(int segs) { return 32 * segs; }
-__host__ __device__ constexpr int tile_h(int segs) { return kWarps * (4 / segs); }
+__host__ __device__ constexpr int tile_h(int segs, int warps) { return warps * (4 / segs); }
 // Tensor-map menu: one map per box shape.
 //   narrow boxes: 12 widths (64..512 B in steps of 64, 640..1024 B in steps of 128) x 16 heights
 //                 (1..8, 10..16 in steps of 2, 20..32 in steps of 4), uint32 elements;
@@ -300,13 +302,14 @@ __device__ __noinline__ void produce(const BoxPlan *plan, const WarpFastMaps *ma
 // item consumed up to and including the current stage.  The producer role rotates over the warps
 // (one elected lane each) so that no warp is slower than the others -- a fixed producer warp
 // paces the whole CTA, because every warp waits on the stages it issues.
+template <int WARPS>
 __device__ __forceinline__ void feed(const LoopCtx &c, int done, uint32_t use, int lane, int warp)
 {
     if (lane != 0) return;
-    const int turn = ((int)use - warp) & (kWarps - 1);
+    const int turn = ((int)use - warp) & (WARPS - 1);
     const int i_load = done + (c.ahead - 1) * c.fps;  // first frame of the stage `ahead` stages on
     if (turn == 0 && i_load < c.n_frames) produce<true>(c.plan, c.maps, i_load, use + c.ahead);
-    if (c.pf && turn == kWarps / 2 && i_load + c.pf * c.fps < c.n_frames)
+    if (c.pf && turn == WARPS / 2 && i_load + c.pf * c.fps < c.n_frames)
         produce<false>(c.plan, c.maps, i_load + c.pf * c.fps, 0);
 }
 
@@ -318,7 +321,7 @@ __device__ __forceinline__ void feed(const LoopCtx &c, int done, uint32_t use, i
 // issued.  Returns the advanced stage counter.
 // started() is run by thread 0 once the first copies of the item are on their way (the decode of
 // the CTA's next item: thread-0 work that would otherwise delay every item's first bytes).
-template <typename BODY, typename STARTED>
+template <int WARPS, typename BODY, typename STARTED>
 __device__ __forceinline__ uint32_t stage_loop(const LoopCtx &c, uint32_t use, uint8_t *d,
                                                const uint32_t d_step, const int tid, BODY body, STARTED started)
 {
@@ -354,7 +357,7 @@ __device__ __forceinline__ uint32_t stage_loop(const LoopCtx &c, uint32_t use, u
                     uint32_t u = use, dn = (uint32_t)done;
                     keep(u);
                     keep(dn);
-                    feed(c, (int)dn, u, lane, warp);
+                    feed<WARPS>(c, (int)dn, u, lane, warp);
                 }
             });
         }
@@ -456,12 +459,13 @@ __device__ __forceinline__ void pair_lerp(const PairReg &q, const PairRow &a0, c
 // MINB = CTAs per SM the register allocation is bounded for (4 -> 64 registers, 3 -> 80);
 // SEGS = tile shape (see tile_w / tile_h).
 template <typename PX, bool LINEAR, int MINB, int SEGS>
-__global__ void __launch_bounds__(kThreads, MINB)
+__global__ void __launch_bounds__((cta_threads<PX, LINEAR>()), MINB)
 warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
                       const __grid_constant__ WarpFastMaps maps,
                       const __grid_constant__ ChunkPlan plan, const int tiles_x, const int tiles_y,
                       const int total_items, const int ring_bytes, const WarpScratch sc)
 {
+    constexpr int kThreads = cta_threads<PX, LINEAR>(), kWarps = kThreads / 32;
     extern __shared__ __align__(128) uint8_t smem[];
     // three barrier sets, one per ring depth S = 2, 4, 8: full[S] then empty[S], at byte
     // offsets 0, 32 and 96.  Each set keeps its own running stage counter (s_use) across items,
@@ -559,7 +563,7 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
         int next_raw = 0;
         if (tid == 0) next_raw = atomicAdd(sc.next_item, 1);
         const int x0 = tile_x * tile_w(SEGS) + warp_px_x<SEGS, kPairMap>(warp);
-        const int y0 = tile_y * tile_h(SEGS) + warp_px_y<SEGS, kPairMap>(warp);
+        const int y0 = tile_y * tile_h(SEGS, kWarps) + warp_px_y<SEGS, kPairMap>(warp);
         const int tile_id = gi * n_tiles + tile_x * tiles_y + tile_y;
         par ^= 1;
 
@@ -842,7 +846,7 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
                 const long long d_second = sw ? -(long long)row_bytes : (long long)row_bytes;
                 uint8_t *d_first = sw ? d + row_bytes : d;
                 if (var == 0) {
-                    use = stage_loop(c, use, d_first, d_step, tid, [&](uint32_t sa, uint8_t *dd, auto release) {
+                    use = stage_loop<kWarps>(c, use, d_first, d_step, tid, [&](uint32_t sa, uint8_t *dd, auto release) {
                         const uint32_t sb = sa + c.pitch;
                         uint32_t P[4];
 #pragma unroll
@@ -862,7 +866,7 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
                         }
                     }, next_item_decode);
                 } else {
-                    use = stage_loop(c, use, d_first, d_step, tid, [&](uint32_t sa, uint8_t *dd, auto release) {
+                    use = stage_loop<kWarps>(c, use, d_first, d_step, tid, [&](uint32_t sa, uint8_t *dd, auto release) {
                         const uint32_t sb = sa + c.pitch, sc2 = sb + c.pitch;
                         uint32_t P[4];
 #pragma unroll
@@ -896,7 +900,7 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
                     keep(px[k].addr);
                     keep(px[k].sh);
                 }
-                use = stage_loop(c, use, d, d_step, tid, [&](uint32_t sa, uint8_t *dd, auto release) {
+                use = stage_loop<kWarps>(c, use, d, d_step, tid, [&](uint32_t sa, uint8_t *dd, auto release) {
                     const uint32_t sb = sa + c.pitch;  // row 1 of the windows
                     typename PX::Out P[4];
 #pragma unroll
@@ -1045,7 +1049,10 @@ struct KernelConfig {
 #ifndef BEVK_LINEAR_CTAS
 #define BEVK_LINEAR_CTAS 3
 #endif
-constexpr int min_ctas(bool linear) { return (linear ? BEVK_LINEAR_CTAS : 4) * (256 / kThreads); }
+template <typename PX, bool LINEAR> constexpr int min_ctas()
+{
+    return (LINEAR ? BEVK_LINEAR_CTAS : 4) * (256 / cta_threads<PX, LINEAR>());
+}
 // Everything that belongs to one device: the kernels' shared-memory opt-in and ring size
 // (cudaFuncSetAttribute is per device), the SM count, the memory-pool set-up.  Guarded by g_map_mutex.
 constexpr int kMaxDevices = 64;
@@ -1082,7 +1089,8 @@ inline int format_bpp(int fmt)
 
 template <typename PX, bool LINEAR, int SEGS> int configure(KernelConfig &cfg)
 {
-    constexpr int kMinCtas = min_ctas(LINEAR);
+    constexpr int kMinCtas = min_ctas<PX, LINEAR>();
+    constexpr int kThreads = cta_threads<PX, LINEAR>();
     auto kern = warp_fast_kernel<PX, LINEAR, kMinCtas, SEGS>;
     // how many CTAs the register file allows, then split the shared memory evenly between them
     BEVK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1024));
@@ -1121,7 +1129,7 @@ template <typename PX, bool LINEAR, int SEGS>
 void launch(int grid, int smem, cudaStream_t stream, const BevkWarpParams &p, const WarpFastMaps &maps,
             const ChunkPlan &plan, int tiles_x, int tiles_y, int items, int ring_bytes, const WarpScratch &sc)
 {
-    warp_fast_kernel<PX, LINEAR, min_ctas(LINEAR), SEGS><<<grid, kThreads, smem, stream>>>(
+    warp_fast_kernel<PX, LINEAR, min_ctas<PX, LINEAR>(), SEGS><<<grid, cta_threads<PX, LINEAR>(), smem, stream>>>(
         p, maps, plan, tiles_x, tiles_y, items, ring_bytes, sc);
 }
 template <typename PX>
@@ -1148,9 +1156,9 @@ void launch_any(int linear, int segs, int grid, int smem, cudaStream_t stream, c
 // widest tensor box, taller than kMaxBoxes boxes, or larger than half the ring.  The box of a tile
 // is spanned by its four corner pixels (a projective map is monotone along lines as long as w
 // keeps its sign); tiles where w changes sign are left out of the estimate (the kernel copes).
-double unstaged_fraction(const BevkWarpParams &p, int linear, int bpp, int segs, int ring_bytes)
+double unstaged_fraction(const BevkWarpParams &p, int linear, int bpp, int segs, int warps, int ring_bytes)
 {
-    const int tw = tile_w(segs), th = tile_h(segs);
+    const int tw = tile_w(segs), th = tile_h(segs, warps);
     const int tiles_x = (p.dst_w + tw - 1) / tw, tiles_y = (p.dst_h + th - 1) / th;
     // up to 16 x 32 evenly spaced tiles, first and last row / column included
     const int nsx = tiles_x < 16 ? tiles_x : 16, nsy = tiles_y < 32 ? tiles_y : 32;
@@ -1202,7 +1210,7 @@ double unstaged_fraction(const BevkWarpParams &p, int linear, int bpp, int segs,
 
 struct ModeKey {
     double M[BEVK_MAX_GROUPS][9];
-    int n_groups, src_h, src_w, dst_h, dst_w, linear, bpp;
+    int n_groups, src_h, src_w, dst_h, dst_w, linear, bpp, warps;
 };
 struct ModeEntry {
     ModeKey key;
@@ -1224,7 +1232,7 @@ unsigned long long g_mode_stamp = 0;
 // untouched pixels, the direct-gather kernel moves less data).
 // *split is set when the chosen shape still leaves a noticeable fraction of the tiles unstaged:
 // those tiles are cheaper in a second, direct-gather launch than in the staged kernel's fallback.
-int pick_tile_shape(const BevkWarpParams &p, int linear, int bpp, int ring_bytes, bool force, bool *split)
+int pick_tile_shape(const BevkWarpParams &p, int linear, int bpp, int warps, int ring_bytes, bool force, bool *split)
 {
     // nearest reads one tap per pixel, so its in-kernel fallback costs little: keep wide tiles
     const double kNegligible = linear ? 0.002 : 0.05;
@@ -1238,6 +1246,7 @@ int pick_tile_shape(const BevkWarpParams &p, int linear, int bpp, int ring_bytes
     key.dst_w = p.dst_w;
     key.linear = linear;
     key.bpp = bpp;
+    key.warps = warps;
     std::lock_guard<std::mutex> lock(g_map_mutex);
     ModeEntry *victim = &g_mode_cache[0];  // an empty entry (stamp 0), else the least recently used
     for (int i = 0; i < kModeCacheSize; ++i) {
@@ -1256,7 +1265,7 @@ int pick_tile_shape(const BevkWarpParams &p, int linear, int bpp, int ring_bytes
     const char *env = getenv("BEVK_FAST_SEGS");  // tuning aid: force a tile shape
     for (int si = 0; si < 3; ++si) {
         if (env && atoi(env) != shapes[si]) continue;
-        const double f = unstaged_fraction(p, linear, bpp, shapes[si], ring_bytes);
+        const double f = unstaged_fraction(p, linear, bpp, shapes[si], warps, ring_bytes);
         if (f < best_frac - 1e-9) {
             best_frac = f;
             best = shapes[si];
@@ -1285,6 +1294,11 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
     const int fmt = format_index(dtype, channels);
     if (fmt < 0) return 0;
     const int bpp = format_bpp(fmt);
+    const int threads = with_format(fmt, [&](auto px) {
+        using PX = decltype(px);
+        return linear ? cta_threads<PX, true>() : cta_threads<PX, false>();
+    });
+    const int warps = threads / 32;
     for (int c = 0; c < channels; ++c)
         if (p_in.border[c] != 0.f) return 0;
     if (p_in.src_w < 2 || p_in.src_h < 2) return 0;
@@ -1334,7 +1348,7 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
         cfg0 = c0;
     }
     bool split = false;
-    const int segs = pick_tile_shape(p, linear, bpp, cfg0.ring_bytes, force != 0, &split);
+    const int segs = pick_tile_shape(p, linear, bpp, warps, cfg0.ring_bytes, force != 0, &split);
     if (segs == 0) return 0;
     {
         std::lock_guard<std::mutex> lock(g_map_mutex);
@@ -1351,7 +1365,7 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
     if (rc) return rc;
 
     const int tiles_x = (p.dst_w + tile_w(segs) - 1) / tile_w(segs);
-    const int tiles_y = (p.dst_h + tile_h(segs) - 1) / tile_h(segs);
+    const int tiles_y = (p.dst_h + tile_h(segs, warps) - 1) / tile_h(segs, warps);
     const long long n_tiles = (long long)tiles_x * tiles_y;
     const int ctas = ds.sm_count * cfg.ctas_per_sm;
 
@@ -1398,13 +1412,13 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
     // other kernels have issue slots to spare and lose a little to the extra round trips (nearest
     // 0.326 -> 0.331 ms), so they recompute.
     const bool share_setup = fmt == 0 && linear && plan.n_chunks > 1 &&
-                             tile_groups * kRecWords * kThreads * 4 <= (512LL << 20) &&
+                             tile_groups * kRecWords * threads * 4 <= (512LL << 20) &&
                              !getenv("BEVK_NO_SETUP_CACHE");
     const size_t off_hard = 256;
     const size_t off_ready = off_hard + (((size_t)(split ? tile_groups : 0) + 255) & ~(size_t)255);
     const size_t off_hdr = off_ready + (((size_t)(share_setup ? tile_groups * 4 : 0) + 255) & ~(size_t)255);
     const size_t off_rec = off_hdr + (share_setup ? (size_t)tile_groups * kHdrInts * 4 : 0);
-    const size_t total = off_rec + (share_setup ? (size_t)tile_groups * kRecWords * kThreads * 4 : 0);
+    const size_t total = off_rec + (share_setup ? (size_t)tile_groups * kRecWords * threads * 4 : 0);
     unsigned char *scratch = nullptr;
     BEVK_CUDA(cudaMallocAsync((void **)&scratch, total, stream));
     cudaError_t e = cudaMemsetAsync(scratch, 0, off_hdr, stream);
@@ -1419,7 +1433,9 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
     sc.recip_tiles_y = recip(tiles_y);
     sc.no_pairs = getenv("BEVK_NO_PAIRS") ? 1 : 0;
     sc.dbg = (kExperiments && getenv("BEVK_DBG")) ? atoi(getenv("BEVK_DBG")) : 0;
-    sc.slack = getenv("BEVK_SLACK") ? atoi(getenv("BEVK_SLACK")) : 0;
+    // stages of the ring NOT in flight ahead of the consumers: half the ring (0) for 8-warp CTAs,
+    // whose warps drift apart; one stage for the 4-warp uint8 x 3 bilinear kernel (cfg 2 0.412 -> 0.407 ms)
+    sc.slack = getenv("BEVK_SLACK") ? atoi(getenv("BEVK_SLACK")) : ((fmt == 0 && linear) ? 1 : 0);
     sc.pf = getenv("BEVK_PF") ? atoi(getenv("BEVK_PF")) : -1;
     sc.pf1 = getenv("BEVK_PF1") ? atoi(getenv("BEVK_PF1")) : kPrefetchAhead;
     sc.max_fps = getenv("BEVK_MAXFPS") ? atoi(getenv("BEVK_MAXFPS")) : kMaxStageFrames;
@@ -1427,7 +1443,7 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
         // one byte per (group, tile): the staged kernel marks the tiles it leaves to the second launch
         p.hard = scratch + off_hard;
         p.hard_tw = tile_w(segs);
-        p.hard_th = tile_h(segs);
+        p.hard_th = tile_h(segs, warps);
         p.hard_ty = tiles_y;
         p.hard_tiles = (int)n_tiles;
     }

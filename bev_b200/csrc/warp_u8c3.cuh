@@ -87,6 +87,7 @@ struct PxU8C3 {
     static constexpr int kBpp = 3;         // bytes per pixel
     static constexpr int kSegBytes = 96;   // bytes of a 32-pixel row segment
     static constexpr int kDtype = BEVK_U8;
+    static constexpr int kLinearThreads = 128, kNearestThreads = 256;  // CTA size of the staged kernel (warp_fast.cu)
     static constexpr int kWinWords = 8;     // window words the kernel keeps per pixel
     static constexpr bool kPairs = true;   // the staged kernel's shared-window pair path exists for this format
     using Reg = Pix;
