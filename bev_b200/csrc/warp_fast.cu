@@ -1046,12 +1046,11 @@ struct KernelConfig {
 // CTAs per SM the register allocation is bounded for: bilinear needs 80 registers per thread (a
 // 64-register build spills in the frame loop and is slower), nearest fits 64 without spilling and
 // gains 5 % from the fourth CTA.
-#ifndef BEVK_LINEAR_CTAS
-#define BEVK_LINEAR_CTAS 3
-#endif
+// CTAs per SM the register allocation of a kernel is bounded for (PX::kLinearCtas for the bilinear
+// kernels; nearest kernels fit 64 registers: 4 CTAs of 8 warps).
 template <typename PX, bool LINEAR> constexpr int min_ctas()
 {
-    return (LINEAR ? BEVK_LINEAR_CTAS : 4) * (256 / cta_threads<PX, LINEAR>());
+    return LINEAR ? PX::kLinearCtas : 4 * (256 / cta_threads<PX, LINEAR>());
 }
 // Everything that belongs to one device: the kernels' shared-memory opt-in and ring size
 // (cudaFuncSetAttribute is per device), the SM count, the memory-pool set-up.  Guarded by g_map_mutex.

@@ -23,6 +23,7 @@ struct PxU8C1 {
     static constexpr int kDtype = BEVK_U8;
     static constexpr bool kPairs = false;
     static constexpr int kLinearThreads = 256, kNearestThreads = 256;
+    static constexpr int kLinearCtas = 3;
     static constexpr int kWinWords = 4;
     using Reg = Pix;       // addr, sh, w0 / w1 = dp2a tap weights of window rows 0 / 1 (nearest: w0 = mask)
     using Out = uint32_t;  // the byte
@@ -94,6 +95,7 @@ struct PxU8C4 {
     static constexpr int kDtype = BEVK_U8;
     static constexpr bool kPairs = false;
     static constexpr int kLinearThreads = 256, kNearestThreads = 256;
+    static constexpr int kLinearCtas = 3;
     static constexpr int kWinWords = 4;
     using Reg = Pix;       // sh unused (0)
     using Out = uint32_t;  // [c0 c1 c2 c3]
@@ -179,6 +181,7 @@ struct PxF32C3 {
     static constexpr int kDtype = BEVK_F32;
     static constexpr bool kPairs = false;
     static constexpr int kLinearThreads = 256, kNearestThreads = 256;
+    static constexpr int kLinearCtas = 3;
     static constexpr int kWinWords = 12;
     using Reg = PixF32;
     struct Out {
