@@ -1406,11 +1406,12 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
     // other threads get their own): [item counter | split flags | set-up ready flags] zeroed, then
     // the tiles' set-up headers and records.
     split = split && !getenv("BEVK_NO_SPLIT");  // env: tuning aid
-    // Sharing a tile's set-up between its frame chunks pays where the set-up is expensive and the
-    // issue slots are the scarce resource: uint8 x 3 bilinear (cfg 2: 0.444 -> 0.428 ms).  The
-    // other kernels have issue slots to spare and lose a little to the extra round trips (nearest
-    // 0.326 -> 0.331 ms), so they recompute.
-    const bool share_setup = fmt == 0 && linear && plan.n_chunks > 1 &&
+    // Sharing a tile's set-up between its frame chunks pays where the set-up is expensive relative to
+    // the per-frame work and the issue slots are the scarce resource: uint8 x 3 bilinear (cfg 2: 0.444 ->
+    // 0.428 ms) and uint8 x 1 bilinear (0.277 -> 0.256 ms).  The other kernels have issue slots to spare
+    // and gain nothing (float16, uint8 x 4, float32) or lose a little to the extra round trips
+    // (nearest 0.326 -> 0.331 ms), so they recompute.
+    const bool share_setup = (fmt == 0 || fmt == 2) && linear && plan.n_chunks > 1 &&
                              tile_groups * kRecWords * threads * 4 <= (512LL << 20) &&
                              !getenv("BEVK_NO_SETUP_CACHE");
     const size_t off_hard = 256;
