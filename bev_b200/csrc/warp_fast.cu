@@ -964,6 +964,15 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
     }
 }
 
+// Tuning switches (BEVK_* environment variables) exist only in -DBEVK_EXPERIMENTS builds; the
+// product build reads no environment on the launch path.
+inline const char *tune_env(const char *name) { return kExperiments ? getenv(name) : nullptr; }
+inline int tune_int(const char *name, int dflt)
+{
+    const char *v = tune_env(name);
+    return v ? atoi(v) : dflt;
+}
+
 // ---- host side: tensor-map menu ---------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
                                   const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
@@ -1261,7 +1270,7 @@ int pick_tile_shape(const BevkWarpParams &p, int linear, int bpp, int warps, int
     int best = 0;
     double best_frac = 2.0;
     static const int shapes[3] = {4, 2, 1};
-    const char *env = getenv("BEVK_FAST_SEGS");  // tuning aid: force a tile shape
+    const char *env = tune_env("BEVK_FAST_SEGS");  // tuning aid: force a tile shape
     for (int si = 0; si < 3; ++si) {
         if (env && atoi(env) != shapes[si]) continue;
         const double f = unstaged_fraction(p, linear, bpp, shapes[si], warps, ring_bytes);
@@ -1375,7 +1384,7 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
     ChunkPlan plan;
     memset(&plan, 0, sizeof(plan));
     const long long tile_groups = n_tiles * p.n_groups;
-    if (const char *env = getenv("BEVK_CHUNKS")) {  // tuning aid: chunk lengths in 1/256ths, e.g. "96,64,48,32,16"
+    if (const char *env = tune_env("BEVK_CHUNKS")) {  // tuning aid: chunk lengths in 1/256ths, e.g. "96,64,48,32,16"
         int k = 0, acc = 0;
         for (const char *q = env; *q && k < kMaxChunks;) {
             acc += atoi(q);
@@ -1405,7 +1414,7 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
     // Per-launch scratch, allocated and freed in stream order (launches on other streams or from
     // other threads get their own): [item counter | split flags | set-up ready flags] zeroed, then
     // the tiles' set-up headers and records.
-    split = split && !getenv("BEVK_NO_SPLIT");  // env: tuning aid
+    split = split && !tune_env("BEVK_NO_SPLIT");
     // Sharing a tile's set-up between its frame chunks pays where the set-up is expensive relative to
     // the per-frame work and the issue slots are the scarce resource: uint8 x 3 bilinear (cfg 2: 0.444 ->
     // 0.428 ms) and uint8 x 1 bilinear (0.277 -> 0.256 ms).  The other kernels have issue slots to spare
@@ -1413,7 +1422,7 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
     // (nearest 0.326 -> 0.331 ms), so they recompute.
     const bool share_setup = (fmt == 0 || fmt == 2) && linear && plan.n_chunks > 1 &&
                              tile_groups * kRecWords * threads * 4 <= (512LL << 20) &&
-                             !getenv("BEVK_NO_SETUP_CACHE");
+                             !tune_env("BEVK_NO_SETUP_CACHE");
     const size_t off_hard = 256;
     const size_t off_ready = off_hard + (((size_t)(split ? tile_groups : 0) + 255) & ~(size_t)255);
     const size_t off_hdr = off_ready + (((size_t)(share_setup ? tile_groups * 4 : 0) + 255) & ~(size_t)255);
@@ -1431,14 +1440,14 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
     sc.recip_per_chunk = recip(tile_groups);
     sc.recip_tiles = recip(n_tiles);
     sc.recip_tiles_y = recip(tiles_y);
-    sc.no_pairs = getenv("BEVK_NO_PAIRS") ? 1 : 0;
-    sc.dbg = (kExperiments && getenv("BEVK_DBG")) ? atoi(getenv("BEVK_DBG")) : 0;
+    sc.no_pairs = tune_env("BEVK_NO_PAIRS") ? 1 : 0;
+    sc.dbg = tune_int("BEVK_DBG", 0);
     // stages of the ring NOT in flight ahead of the consumers: half the ring (0) for 8-warp CTAs,
     // whose warps drift apart; one stage for the 4-warp uint8 x 3 bilinear kernel (cfg 2 0.412 -> 0.407 ms)
-    sc.slack = getenv("BEVK_SLACK") ? atoi(getenv("BEVK_SLACK")) : ((fmt == 0 && linear) ? 1 : 0);
-    sc.pf = getenv("BEVK_PF") ? atoi(getenv("BEVK_PF")) : -1;
-    sc.pf1 = getenv("BEVK_PF1") ? atoi(getenv("BEVK_PF1")) : kPrefetchAhead;
-    sc.max_fps = getenv("BEVK_MAXFPS") ? atoi(getenv("BEVK_MAXFPS")) : kMaxStageFrames;
+    sc.slack = tune_int("BEVK_SLACK", (fmt == 0 && linear) ? 1 : 0);
+    sc.pf = tune_int("BEVK_PF", -1);
+    sc.pf1 = tune_int("BEVK_PF1", kPrefetchAhead);
+    sc.max_fps = tune_int("BEVK_MAXFPS", kMaxStageFrames);
     if (split) {
         // one byte per (group, tile): the staged kernel marks the tiles it leaves to the second launch
         p.hard = scratch + off_hard;
