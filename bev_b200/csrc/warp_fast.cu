@@ -147,6 +147,7 @@ struct WarpScratch {
     int pf;           // L2 prefetch distance in stages beyond the fills (-1: depth-2 rings only, 2 stages)
     int pf1;          // the same for depth-2 rings when pf < 0
     int max_fps;      // frames per ring stage, at most
+    unsigned long long *prof;  // -DBEVK_EXPERIMENTS builds only (BEVK_PROF): cycle counters of thread 0
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -218,7 +219,7 @@ __device__ __forceinline__ void st_release(int *p, int v)
 // Stops the compiler from re-deriving a loop-invariant value inside the frame loop.
 __device__ __forceinline__ void keep(uint32_t &v) { asm volatile("" : "+r"(v)); }
 
-// What the elected producer thread needs to fetch one frame's bounding box.
+// What the producing warp needs to fetch the frames' bounding boxes.
 struct BoxPlan {
     int n_boxes;
     int x;                  // first column, in elements of the map (TMA wants 16-byte aligned box rows)
@@ -245,7 +246,7 @@ struct ItemDesc {
 };
 
 // The consumers' loop state (kept small so that the frame loop fits its register budget); the
-// elected producer lane reads what it needs from the BoxPlan in shared memory.
+// producing warp reads what it needs from the BoxPlan in shared memory.
 struct LoopCtx {
     uint32_t ring, full0;          // shared-memory addresses of the ring / first barrier of the set
     uint32_t stride;               // bytes per stage (fps frames)
@@ -257,68 +258,67 @@ struct LoopCtx {
     int ahead;                     // stages in flight ahead of the one being consumed
     int pf;                        // L2 prefetch distance in stages beyond that (0: none)
     int dbg;
+    unsigned long long *prof;      // -DBEVK_EXPERIMENTS builds (BEVK_PROF): cycle counters of thread 0
     const WarpFastMaps *maps;
     const BoxPlan *plan;           // in shared memory
 };
 
-// Elected thread: pull the stage that starts at frame i0 of the item towards the SM.  TO_SMEM
-// starts the copies into its ring slot (`use` is the running count of stages this CTA has pushed
-// through the barrier set); otherwise the boxes are only prefetched into L2 so that the later
-// copy does not wait on HBM (used by depth-2 rings, whose copies run just one stage ahead).
-// Deliberately not inlined: it runs in one lane of one warp per stage and must not cost the
-// frame loop registers.
+// One warp pulls the stage that starts at frame i0 of the item towards the SM: lane l issues box
+// (l % n_boxes) of the stage's frame (l / n_boxes), so all requests of a stage (at most
+// kMaxStageFrames * kMaxBoxes = 24) leave in one pass.  TO_SMEM starts the copies into the stage's
+// ring slot (`use` is the running count of stages this CTA has pushed through the barrier set);
+// otherwise the boxes are only prefetched into L2 so that the later copy does not wait on HBM
+// (used by depth-2 rings, whose copies run just one stage ahead).  Deliberately not inlined: it
+// runs in one warp per stage and must not cost the frame loop registers.
 template <bool TO_SMEM>
 __device__ __noinline__ void produce(const BoxPlan *plan, const WarpFastMaps *maps, int i0,
-                                     uint32_t use)
+                                     uint32_t use, int lane)
 {
     const BoxPlan &pl = *plan;
     const int nf = min(pl.fps, pl.n_frames - i0);
     const int nb = pl.n_boxes;
-    int y = (pl.frame0 + i0 * pl.frame_step) * pl.src_h + pl.y0;
-    const int y_step = pl.frame_step * pl.src_h;
+    const int f = nb == 1 ? lane : (nb == 2 ? lane >> 1 : (lane * 11) >> 5);  // lane / 3 for lane < 32
+    const int b = lane - f * nb;
+    const bool mine = f < nf;
+    const int row = pl.row[mine ? b : 0];
+    const CUtensorMap *map = &maps->m[pl.map_idx[mine ? b : 0]];
+    const int y = (pl.frame0 + (i0 + f) * pl.frame_step) * pl.src_h + pl.y0 + row;
     if (TO_SMEM) {
         const uint32_t slot = use & ((1u << pl.slog) - 1u);
         const uint32_t fb = pl.full0 + 8 * slot;
         // k-th fill of a slot waits for the (k-1)-th release; the first passes at once
         mbar_wait(fb + (8u << pl.slog), ((use >> pl.slog) & 1u) ^ 1u);
-        mbar_expect_tx(fb, pl.bytes * nf);
-        uint32_t sdst = pl.ring + slot * pl.stride;
-#pragma unroll 1
-        for (int f = 0; f < nf; ++f, sdst += pl.frame_bytes, y += y_step)
-#pragma unroll 1
-            for (int b = 0; b < nb; ++b)
-                tma_box_g2s(sdst + pl.row[b] * pl.pitch, &maps->m[pl.map_idx[b]], pl.x,
-                            y + pl.row[b], fb);
-    } else {
-#pragma unroll 1
-        for (int f = 0; f < nf; ++f, y += y_step)
-#pragma unroll 1
-            for (int b = 0; b < nb; ++b)
-                tma_box_prefetch(&maps->m[pl.map_idx[b]], pl.x, y + pl.row[b]);
+        if (lane == 0) mbar_expect_tx(fb, pl.bytes * nf);
+        __syncwarp();
+        if (mine)
+            tma_box_g2s(pl.ring + slot * pl.stride + f * pl.frame_bytes + row * pl.pitch, map, pl.x, y, fb);
+    } else if (mine) {
+        tma_box_prefetch(map, pl.x, y);
     }
 }
 
 // Keep the ring (and, for depth-2 rings, the L2 prefetch window) full.  `done` = frames of the
 // item consumed up to and including the current stage.  The producer role rotates over the warps
-// (one elected lane each) so that no warp is slower than the others -- a fixed producer warp
-// paces the whole CTA, because every warp waits on the stages it issues.
+// so that no warp is slower than the others -- a fixed producer warp paces the whole CTA, because
+// every warp waits on the stages it issues.  (It is in effect the fastest warps that produce: the
+// refill of a slot waits for the slowest warp to release it.  Handing the refill to the warp that
+// releases a slot last was tried: 7 % slower, it loads the warp that is already behind.)
 template <int WARPS>
 __device__ __forceinline__ void feed(const LoopCtx &c, int done, uint32_t use, int lane, int warp)
 {
-    if (lane != 0) return;
     const int turn = ((int)use - warp) & (WARPS - 1);
     const int i_load = done + (c.ahead - 1) * c.fps;  // first frame of the stage `ahead` stages on
-    if (turn == 0 && i_load < c.n_frames) produce<true>(c.plan, c.maps, i_load, use + c.ahead);
+    if (turn == 0 && i_load < c.n_frames) produce<true>(c.plan, c.maps, i_load, use + c.ahead, lane);
     if (c.pf && turn == WARPS / 2 && i_load + c.pf * c.fps < c.n_frames)
-        produce<false>(c.plan, c.maps, i_load + c.pf * c.fps, 0);
+        produce<false>(c.plan, c.maps, i_load + c.pf * c.fps, 0, lane);
 }
 
-// The frame loop of a staged item: ring of 2^slog stages of c.fps frames each, half of them in
-// flight ahead of the stage being consumed -- the other half is slack between the warps (a slot is
-// refilled S/2 stages after its last use, so the refilling lane practically never waits for a
-// slower warp to release it).  body(sa, d, release) interpolates the thread's pixels of ONE frame
-// staged at shared address sa into d; it calls release() once all its shared-memory reads are
-// issued.  Returns the advanced stage counter.
+// The frame loop of a staged item: ring of 2^slog stages of c.fps frames each, c.ahead of them in
+// flight ahead of the stage being consumed, the rest slack between the warps.  body(sa, d)
+// interpolates the thread's pixels of ONE frame staged at shared address sa into d.  A warp hands
+// a slot back once it is through the stage's last frame (testing for the last frame inside the
+// body, to release a little earlier, costs more than it gains: the frame loop is one straight
+// block this way).  Returns the advanced stage counter.
 // started() is run by thread 0 once the first copies of the item are on their way (the decode of
 // the CTA's next item: thread-0 work that would otherwise delay every item's first bytes).
 template <int WARPS, typename BODY, typename STARTED>
@@ -327,39 +327,35 @@ __device__ __forceinline__ uint32_t stage_loop(const LoopCtx &c, uint32_t use, u
 {
     const uint32_t smask = (1u << c.slog) - 1u;
     const int lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
-        if (!(kExperiments && (c.dbg & 2))) {
+    const bool live = !(kExperiments && (c.dbg & 2));
+    if (warp == 0) {
+        if (live) {
             for (int s = 0; s < c.ahead && s * c.fps < c.n_frames; ++s)
-                produce<true>(c.plan, c.maps, s * c.fps, use + s);
+                produce<true>(c.plan, c.maps, s * c.fps, use + s, lane);
             for (int s = c.ahead; s < c.ahead + c.pf && s * c.fps < c.n_frames; ++s)
-                produce<false>(c.plan, c.maps, s * c.fps, 0);
+                produce<false>(c.plan, c.maps, s * c.fps, 0, lane);
         }
-        started();
+        if (tid == 0) started();
     }
     int done = 0;
 #pragma unroll 1
     while (done < c.n_frames) {
         const uint32_t slot = use & smask;
         const uint32_t fb = c.full0 + 8 * slot;
-        if (!(kExperiments && (c.dbg & 2))) mbar_wait(fb, (use >> c.slog) & 1u);
+        long long tw0 = 0;
+        if (kExperiments && c.prof && tid == 0) tw0 = clock64();
+        if (live) mbar_wait(fb, (use >> c.slog) & 1u);
+        if (kExperiments && c.prof && tid == 0)
+            atomicAdd(c.prof + (done == 0 ? 1 : 2), (unsigned long long)(clock64() - tw0));
         uint32_t sa = c.ring + slot * c.stride;  // first frame of the stage
         int nf = min(c.fps, c.n_frames - done);
         done += nf;
 #pragma unroll 1
-        for (; nf > 0; --nf, sa += c.frame_bytes, d += d_step) {
-            body(sa, d, [&]() {
-                if (nf == 1 && !(kExperiments && (c.dbg & 2))) {
-                    // every shared-memory read of this stage is issued: hand the slot back
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(fb + (8u << c.slog));
-                    // (through keep(): whose turn it is gets worked out here, once per stage, and
-                    // not hoisted into predicates that stay live across the frame loop)
-                    uint32_t u = use, dn = (uint32_t)done;
-                    keep(u);
-                    keep(dn);
-                    feed<WARPS>(c, (int)dn, u, lane, warp);
-                }
-            });
+        for (; nf > 0; --nf, sa += c.frame_bytes, d += d_step) body(sa, d);
+        if (live) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(fb + (8u << c.slog));
+            feed<WARPS>(c, done, use, lane, warp);
         }
         ++use;
     }
@@ -566,6 +562,8 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
         const int y0 = tile_y * tile_h(SEGS, kWarps) + warp_px_y<SEGS, kPairMap>(warp);
         const int tile_id = gi * n_tiles + tile_x * tiles_y + tile_y;
         par ^= 1;
+        long long t_item = 0;
+        if (kExperiments && sc.prof && tid == 0) t_item = clock64();
 
         // ---- 1. set-up: window position and tap weights of the thread's four pixels, the tile's
         //         source bounding box -- computed by the tile's first chunk, re-read by the others
@@ -772,12 +770,18 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
             c.ahead = sc.slack ? max(1, (1 << slog) - sc.slack) : (1 << (slog - 1));
             c.pf = sc.pf >= 0 ? sc.pf : (slog == 1 ? sc.pf1 : 0);
             c.dbg = sc.dbg;
+            c.prof = sc.prof;
             c.maps = &maps;
             c.plan = &s_plan;
             keep(c.ring);
             keep(c.full0);
             // every thread tracks the counter in a register; thread 0 publishes it for the next item
             uint32_t use = s_use[slog - 1];
+            long long t_loop = 0;
+            if (kExperiments && sc.prof && tid == 0) {
+                t_loop = clock64();
+                atomicAdd(sc.prof + 0, (unsigned long long)(t_loop - t_item));  // set-up
+            }
 
             // Pair path (uint8 x 3 bilinear): can every vertical pair of this warp share its
             // window loads?  Needs windows at most one column apart and the same row step --
@@ -846,14 +850,13 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
                 const long long d_second = sw ? -(long long)row_bytes : (long long)row_bytes;
                 uint8_t *d_first = sw ? d + row_bytes : d;
                 if (var == 0) {
-                    use = stage_loop<kWarps>(c, use, d_first, d_step, tid, [&](uint32_t sa, uint8_t *dd, auto release) {
+                    use = stage_loop<kWarps>(c, use, d_first, d_step, tid, [&](uint32_t sa, uint8_t *dd) {
                         const uint32_t sb = sa + c.pitch;
                         uint32_t P[4];
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
                             const PairRow r0 = pair_row(pr[j].addr + sa, pr[j].sh);
                             const PairRow r1 = pair_row(pr[j].addr + sb, pr[j].sh);
-                            if (j == 1) release();
                             const uint32_t y0 = prmt(r0.u, r0.w2, pr[j].sel_y), y1 = prmt(r1.u, r1.w2, pr[j].sel_y);
                             pair_lerp(pr[j], r0, r1, r0, r1, y0, y1, y0, y1, P[2 * j], P[2 * j + 1]);
                         }
@@ -866,7 +869,7 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
                         }
                     }, next_item_decode);
                 } else {
-                    use = stage_loop<kWarps>(c, use, d_first, d_step, tid, [&](uint32_t sa, uint8_t *dd, auto release) {
+                    use = stage_loop<kWarps>(c, use, d_first, d_step, tid, [&](uint32_t sa, uint8_t *dd) {
                         const uint32_t sb = sa + c.pitch, sc2 = sb + c.pitch;
                         uint32_t P[4];
 #pragma unroll
@@ -874,7 +877,6 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
                             const PairRow r0 = pair_row(pr[j].addr + sa, pr[j].sh);
                             const PairRow r1 = pair_row(pr[j].addr + sb, pr[j].sh);
                             const PairRow r2 = pair_row(pr[j].addr + sc2, pr[j].sh);
-                            if (j == 1) release();
                             const uint32_t y0 = prmt(r0.u, r0.w2, pr[j].sel_y), y1 = prmt(r1.u, r1.w2, pr[j].sel_y);
                             const uint32_t y2 = prmt(r2.u, r2.w2, pr[j].sel_y);
                             pair_lerp(pr[j], r0, r1, r1, r2, y0, y1, y1, y2, P[2 * j], P[2 * j + 1]);
@@ -900,7 +902,7 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
                     keep(px[k].addr);
                     keep(px[k].sh);
                 }
-                use = stage_loop<kWarps>(c, use, d, d_step, tid, [&](uint32_t sa, uint8_t *dd, auto release) {
+                use = stage_loop<kWarps>(c, use, d, d_step, tid, [&](uint32_t sa, uint8_t *dd) {
                     const uint32_t sb = sa + c.pitch;  // row 1 of the windows
                     typename PX::Out P[4];
 #pragma unroll
@@ -909,7 +911,6 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
                         const uint32_t a = px[k].addr + sa, b = px[k].addr + sb;
                         PX::template load<LINEAR>(px[k], a, b, a + kLast, b + kLast, w,
                                                   [](uint32_t ad) { return lds32(ad); });
-                        if (k == 3) release();
                         P[k] = PX::template math<LINEAR>(px[k], w);
                     }
                     // pack the lanes' pixels into words and store coalesced row segments
@@ -917,8 +918,15 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
                     for (int k = 0; k < 4; ++k) PX::store(seg_ptr(dd, dd + row_bytes, k), P[k], seg_ok[k], st, lane);
                 }, next_item_decode);
             }
+            long long t_end = 0;
+            if (kExperiments && sc.prof && tid == 0) t_end = clock64();
             __syncthreads();  // every warp has read s_use and left the ring
             if (tid == 0) s_use[slog - 1] = use;
+            if (kExperiments && sc.prof && tid == 0) {
+                atomicAdd(sc.prof + 3, (unsigned long long)(t_end - t_loop));         // frame loops incl. waits
+                atomicAdd(sc.prof + 4, (unsigned long long)(clock64() - t_end));      // end-of-item barrier (warp skew)
+                atomicAdd(sc.prof + 5, 1ULL);
+            }
             continue;
         } else if (p.hard) {
             // split launch: leave the tile to the direct-gather kernel that follows on the stream
@@ -1448,6 +1456,7 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
     sc.pf = tune_int("BEVK_PF", -1);
     sc.pf1 = tune_int("BEVK_PF1", kPrefetchAhead);
     sc.max_fps = tune_int("BEVK_MAXFPS", kMaxStageFrames);
+    sc.prof = tune_env("BEVK_PROF") ? (unsigned long long *)(scratch + 64) : nullptr;  // (zeroed with the item counter)
     if (split) {
         // one byte per (group, tile): the staged kernel marks the tiles it leaves to the second launch
         p.hard = scratch + off_hard;
@@ -1471,6 +1480,13 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
             rc2 = bevk_plan_generic_chunks(p, channels);
             if (!rc2) rc2 = bevk_launch_warp_generic(p, channels, dtype, linear, stream);
         }
+    }
+    if (kExperiments && sc.prof) {  // BEVK_PROF: where thread 0 of every CTA spent its cycles
+        unsigned long long h[8];
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(h, sc.prof, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "BEVK_PROF thread-0 cycles: set-up %llu first-wait %llu later-waits %llu loops %llu end-barrier %llu items %llu (grid %d)\n",
+                h[0], h[1], h[2], h[3], h[4], h[5], grid);
     }
     const cudaError_t ef = cudaFreeAsync(scratch, stream);  // stream-ordered: after the kernels above
     if (e != cudaSuccess) {

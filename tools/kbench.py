@@ -23,10 +23,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--path", default="auto")
     ap.add_argument("--check", action="store_true", help="compare frame 0 and the last frame with the oracle")
+    ap.add_argument("--lib", default=None, help="a variant library built by tools/ab_build.sh (A/B runs)")
     ap.add_argument("workloads", nargs="*")
     args = ap.parse_args()
     wls = args.workloads or ["cfg2_1080p_to_bev1024_u8c3_bilinear_x256", "cfg2_nearest",
                              "cfg5_4k_to_bev2048_u8c3_x64", "cfg5_inv_bev2048_to_4k_u8c3_x64"]
+    if args.lib:
+        _native.LIB_PATH = os.path.abspath(args.lib)
     _native.set_warp_path(args.path)
     peak, _ = bench.measured_peak()
     dev = torch.device("cuda", 0)
