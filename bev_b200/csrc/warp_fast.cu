@@ -767,7 +767,11 @@ warp_fast_kernel(const __grid_constant__ BevkWarpParams p,
             c.fps = fps;
             c.n_frames = n_frames;
             c.slog = slog;
-            c.ahead = sc.slack ? max(1, (1 << slog) - sc.slack) : (1 << (slog - 1));
+            // stages in flight ahead of the one being consumed.  Two-slot rings refill the slot that was
+            // just released (the producing warp waits for the other warps' release), so that the copy of
+            // stage n + 2 runs under stage n + 1 -- with one stage ahead the copy only started when the
+            // frame before it was done (cfg 5 0.424 -> 0.393 ms, cfg 2 0.391 -> 0.382 ms).
+            c.ahead = slog == 1 ? 2 : (sc.slack > 0 ? max(1, (1 << slog) - sc.slack) : (sc.slack < 0 ? (1 << slog) : (1 << (slog - 1))));
             c.pf = sc.pf >= 0 ? sc.pf : (slog == 1 ? sc.pf1 : 0);
             c.dbg = sc.dbg;
             c.prof = sc.prof;
@@ -1450,9 +1454,11 @@ int bevk_launch_warp_fast(const BevkWarpParams &p_in, int channels, int dtype, i
     sc.recip_tiles_y = recip(tiles_y);
     sc.no_pairs = tune_env("BEVK_NO_PAIRS") ? 1 : 0;
     sc.dbg = tune_int("BEVK_DBG", 0);
-    // stages of the ring NOT in flight ahead of the consumers: half the ring (0) for 8-warp CTAs,
-    // whose warps drift apart; one stage for the 4-warp uint8 x 3 bilinear kernel (cfg 2 0.412 -> 0.407 ms)
-    sc.slack = tune_int("BEVK_SLACK", (fmt == 0 && linear) ? 1 : 0);
+    // stages of the ring NOT in flight ahead of the consumers: one (0 = half the ring, < 0 = none).
+    // With a whole warp issuing a stage in one pass the producer's detour is short, and every kernel
+    // does best with all but one stage in flight (float16 cfg 5 0.792 -> 0.749 ms, uint8 x 4 0.441 ->
+    // 0.430 ms, nearest 0.316 -> 0.310 ms); none as slack is worse again for the 4-warp kernels.
+    sc.slack = tune_int("BEVK_SLACK", 1);
     sc.pf = tune_int("BEVK_PF", -1);
     sc.pf1 = tune_int("BEVK_PF1", kPrefetchAhead);
     sc.max_fps = tune_int("BEVK_MAXFPS", kMaxStageFrames);

@@ -5,7 +5,9 @@ import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench
-from bev_b200 import homo
+from bev_b200 import homo, _native
+if os.environ.get("ZLIB"):
+    _native.LIB_PATH = os.path.abspath(os.environ["ZLIB"])
 
 dev = torch.device("cuda", 0)
 g = torch.Generator(device=dev).manual_seed(1234)
