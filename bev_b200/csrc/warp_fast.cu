@@ -2,29 +2,32 @@
 // cv2.warpPerspective on BGR video frames, reference vis_homo.py:85-91), sm_100a.
 //
 // The kernel is written against a pixel-format policy PX (warp_u8c3.cuh: uint8 x 3,
-// warp_f16c3.cuh: float16 x 3) that owns the per-pixel registers, the window loads, the
-// interpolation and the store packing.
+// warp_f16c3.cuh: float16 x 3, warp_formats.cuh: uint8 x 1, uint8 x 4, float32 x 3) that owns the
+// per-pixel registers, the window loads, the interpolation and the store packing.
 //
-// Work item = (chunk of frames, homography group, dst tile).  A persistent CTA of 8 warps pulls
-// items from a shared counter; a tile is 1024 dst pixels, 4 per thread, as 128x8, 64x16 or 32x32
-// (picked per launch on the host, pick_tile_shape):
+// Work item = (chunk of frames, homography group, dst tile).  A persistent CTA of 4 or 8 warps (a
+// constant of the pixel-format policy) pulls items from a counter in the launch's scratch; a tile
+// is 128 dst pixels per warp, 4 per thread, as 128xN, 64x2N or 32x4N (picked per launch on the
+// host, pick_tile_shape):
 //
 //   1. set-up, once per item: the exact FP64 coordinate pipeline of cv2 (bevk_map_pixel_xb) gives
 //      each pixel its 2x2 source window, and frame-invariant registers are derived from it -- the
 //      shared-memory offset of the window, a funnel-shift amount that byte-aligns it and the tap
 //      weights laid out as the policy's operands.  Out-of-image taps get weight 0 and a clamped
 //      address, so the frame loop has no border branches.  A block reduction yields the tile's
-//      source bounding box.
+//      source bounding box.  (uint8 bilinear: the tile's first chunk publishes positions, weights
+//      and box in the scratch, the other chunks re-read them.)
 //   2. frame loop: the bounding box of the next frames is fetched by the TMA unit as 2-D tensor
 //      boxes (cp.async.bulk.tensor.2d, at most 3 requests per frame and tile, completion on an
-//      mbarrier) into a 2-, 4- or 8-deep shared-memory ring of up to 4 frames per stage while the
+//      mbarrier) into a 2-, 4- or 8-deep shared-memory ring of up to 8 frames per stage while the
 //      warps interpolate the current frames out of shared memory.  The producer role rotates over
-//      the warps (one elected lane); full[] / empty[] mbarriers are the only synchronisation in
-//      the loop.  The box shape is picked per tile from a menu of 224 tensor maps over the source
-//      batch viewed as a [frames*rows][row_bytes/4] uint32 (or /8 uint64) matrix: widths
-//      64..2048 B, heights 1..32 rows.  A first version issued one cp.async.bulk per source row:
-//      the TMA unit retired only one such ~300-byte request per ~70 cycles per SM, which capped
-//      the kernel at 33 % of the HBM roofline (profiles/r01_fast_v1_*).
+//      the warps; the warp whose turn it is issues a whole stage in one pass (one lane per frame
+//      and box); full[] / empty[] mbarriers are the only synchronisation in the loop, and all but
+//      one stage of the ring are in flight.  The box shape is picked per tile from a menu of 224
+//      tensor maps over the source batch viewed as a [frames*rows][row_bytes/4] uint32 (or /8
+//      uint64) matrix: widths 64..2048 B, heights 1..32 rows.  A first version issued one
+//      cp.async.bulk per source row: the TMA unit retired only one such ~300-byte request per ~70
+//      cycles per SM, which capped the kernel at 33 % of the HBM roofline (profiles/r01_fast_v1_*).
 //   3. stores: the policy packs the lanes' pixels into words (one shuffle + PRMT for uint8) and
 //      writes fully coalesced row segments with streaming stores.
 //
@@ -35,9 +38,10 @@
 // the marked tiles; above that the whole launch goes to the direct-gather kernel.
 //
 // HBM traffic per frame is the touched source footprint (bounding boxes overlap by a row /
-// column and are re-served by L2: tiles are walked column-major so that neighbours run
-// concurrently and near-/far-field tiles mix) plus the output, i.e. about 1.1x the algorithmic
-// bytes of SURVEY.md 8d.  The binding resource is the shared-memory data pipe.
+// column and are partly re-served by L2: tiles are walked column-major so that neighbours run
+// concurrently, and the frame chunks keep the CTAs within a few dozen frames of each other) plus
+// the output, about 1.2x the algorithmic bytes of SURVEY.md 8d.  What bounds the kernel is
+// instruction issue (75 % of the slots, 0.31 of its 0.38 ms on cfg 2), see DESIGN.md 3.1.
 #include "bevk_common.cuh"
 #include "warp_u8c3.cuh"
 #include "warp_f16c3.cuh"
