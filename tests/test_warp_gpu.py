@@ -268,6 +268,28 @@ def test_staged_kernel_box_shapes(flags, dtype):
         _native.set_warp_path("auto")
 
 
+@pytest.mark.parametrize("dtype", ["uint8", "float16"])
+def test_staged_kernel_long_runs_through_shallow_rings(dtype):
+    """Many frames through the ring shapes that hold few of them: two-slot rings of single frames
+    (boxes of a third of the ring: the slot just released is refilled while the other one is
+    consumed) and frames of several tensor boxes, 29 frames each (a stage count that fills no ring
+    evenly), every frame against the oracle."""
+    _native.set_warp_path("fast")
+    try:
+        rng = np.random.default_rng(11)
+        frames = np.stack([util.seeded_frame(900 + i, 540, 960, 3, dtype) for i in range(29)])
+        quad = np.array([[0, 0], [959, 0], [959, 539], [0, 539]], np.float64)
+        for (dw, dh), jitter in [((256, 256), 0.0), ((512, 120), 6.0), ((1000, 12), 10.0)]:
+            d = np.array([[0, 0], [dw - 1, 0], [dw - 1, dh - 1], [0, dh - 1]], np.float64)
+            H = homo.homo_from_pts(quad + rng.normal(size=(4, 2)) * jitter, d)
+            out = gpu_warp(frames, H, (dw, dh), 1)
+            for i in range(len(frames)):
+                ref = wo.warp_perspective(frames[i], H, (dw, dh), 1)
+                assert util.bits_equal(out[i], ref), ((dw, dh), i)
+    finally:
+        _native.set_warp_path("auto")
+
+
 @pytest.mark.parametrize("flags", [1, 0])
 def test_cfg2_full_batch(flags):
     """BASELINE configs[1] at full size: 256 x 1080p -> 1024^2 in one call.  Three frames are
